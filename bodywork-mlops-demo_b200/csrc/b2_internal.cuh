@@ -1,0 +1,101 @@
+// b2_internal.cuh -- shared declarations of libb2gram.so (not part of the public C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b2gram.h"
+
+namespace b2 {
+
+constexpr int kMaxD = B2_MAX_D;          // 128 features
+constexpr int kMaxS = kMaxD + 2;         // 130: features, ones, y
+constexpr int kKernelEventPairs = 64;
+
+// ---- tcgen05 Gram kernel geometry (gram_tc.cu) ------------------------------------------
+constexpr int kTcRows = 32;              // rows of X per pipeline stage (MMA K = 2 x 16)
+constexpr int kTcM = 128;                // MMA M: feature index (zero padded)
+constexpr int kTcN = 256;                // MMA N: [hi | lo] feature index
+constexpr int kTcAccElems = kTcM * kTcN; // fp32 accumulators drained per chunk
+constexpr int kTcXformWarps = 8;
+constexpr int kTcSideDoubles = kTcXformWarps * 32 * 2 + 8;  // per-CTA side sums (s1,sxy per thread) + y sums
+
+void set_error(const char* fmt, ...);
+
+#define B2_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      b2::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return B2_E_CUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+
+}  // namespace b2
+
+struct b2_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t hbm_bytes = 0;
+  char name[128] = {0};
+  cudaStream_t stream = nullptr;       // compute stream (all kernels)
+  cudaStream_t copy_stream = nullptr;  // H2D staging for B2_MEM_HOST
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_k[b2::kKernelEventPairs][2];
+  int k_pairs = 0;                     // pairs recorded since the last b2_last_kernel_ms
+  int k_launches = 0;                  // kernels launched by the most recent accumulate
+  int64_t launches = 0;                // kernels launched since ctx creation
+
+  int kernel_mode = B2_KERNEL_AUTO;
+  int drain_rows = 8192;
+
+  int d = 0;                           // feature count of the current statistic (0 = not reset)
+  double* S = nullptr;                 // device, kMaxS*kMaxS (only (d+2)^2 used, row stride d+2)
+
+  // tcgen05 path scratch
+  double* tc_part = nullptr;           // [sm_count][kTcAccElems]   per-CTA fp64 partial Gram (col-major)
+  double* tc_side = nullptr;           // [sm_count][kTcSideDoubles]
+  double* tc_red = nullptr;            // [kTcAccElems + 2*kMaxD + 8] reduced over CTAs
+  float* shift = nullptr;              // [64][kMaxD + 1] partial sums of the row sample -> per-column shift c
+  bool tc_attr_set = false;
+  // SIMT path scratch
+  double* simt_part = nullptr;         // [simt_ctas][kMaxS*kMaxS]
+  int simt_ctas = 0;
+  // scoring scratch
+  double* score_part = nullptr;        // [score_ctas][6]
+  int score_ctas = 0;
+  double* coef_dev = nullptr;          // [kMaxD + 1]
+  // solve scratch
+  double* solve_out = nullptr;         // [kMaxD + 2 + kMaxD]: coef, intercept, info, singular
+  double* solve_work = nullptr;        // [2 * kMaxD * kMaxD] eigenvectors etc.
+  // host staging ring (B2_MEM_HOST)
+  void* stage_x[2] = {nullptr, nullptr};
+  float* stage_y[2] = {nullptr, nullptr};
+  uint8_t* stage_m[2] = {nullptr, nullptr};
+  size_t stage_bytes_x = 0;
+  int64_t stage_rows = 0;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  // NCCL
+  void* comm = nullptr;
+  int n_ranks = 1, rank = 0;
+};
+
+namespace b2 {
+
+// ---- kernel launchers (each enqueues on ctx->stream and bumps ctx->launches) -----------------
+int launch_gram_simt(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
+                     int64_t ldx, const uint8_t* mask, int keep);
+bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx);
+int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
+                   int64_t ldx, const uint8_t* mask, int keep);
+int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept);
+int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept);
+int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx,
+                 const float* y, const uint8_t* mask, int keep, float* yhat, bool first_block);
+int launch_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int d, int64_t ldx,
+                 int x_dtype, double alpha, double beta, double sigma, void* X, float* y);
+
+}  // namespace b2

@@ -1,0 +1,218 @@
+"""B200 drop-in for the reference's ``mlops_simulation/stage_1_train_model.py``.
+
+Same stage contract (bodywork.yaml:8-26): run with no arguments, log to stdout, exit 0 / 1;
+same function names and return shapes as the reference module:
+
+==========================  ======================================  ================================
+here                        reference (stage_1_train_model.py)      what changed
+==========================  ======================================  ================================
+``main``                    :31-36                                  unchanged sequence
+``download_latest_dataset`` :39-76                                  a local directory stands in for the
+                                                                    S3 bucket (same keys, same date regex)
+``model_metrics``           :79-90                                  reductions on the GPU (b2_score)
+``train_model``             :93-108                                 split -> row mask; fit / predict /
+                                                                    metrics on the GPU (libb2gram.so)
+``persist_model``           :111-125                                same joblib file of a real sklearn
+                                                                    LinearRegression; copied under models/
+``persist_metrics``         :128-142                                same CSV schema; copied under
+                                                                    model-metrics/
+``configure_logger``        :145-158                                same format string
+==========================  ======================================  ================================
+
+The "bucket" is the directory named by ``$B2_BUCKET_DIR`` (default ``./bodywork-mlops-project``)
+holding ``datasets/regression-dataset-YYYY-MM-DD.csv`` (columns ``date,y,X`` as written by
+stage_3_synthetic_data_generation.py:42,49-50; several features generalise to ``X0..X{D-1}``).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import re
+import shutil
+import sys
+from datetime import date, datetime
+from typing import List, Tuple
+
+import numpy as np
+import pandas as pd
+from joblib import dump
+
+from . import _native as native
+from .estimator import B200LinearRegression, default_context
+
+BUCKET_DIR = os.environ.get("B2_BUCKET_DIR", "bodywork-mlops-project")
+_DATE_RE = re.compile("20[2-9][0-9]-[0-1][0-9]-[0-3][0-9]")  # stage_1_train_model.py:47
+
+log = logging.getLogger(__name__)
+
+
+def main() -> None:
+    """Main script to be executed (stage_1_train_model.py:31-36)."""
+    data, data_date = download_latest_dataset(BUCKET_DIR)
+    model, metrics = train_model(data)
+    persist_model(model, data_date, BUCKET_DIR)
+    persist_metrics(metrics, data_date, BUCKET_DIR)
+
+
+def _date_from_key(key: str) -> date:
+    return datetime.strptime(_DATE_RE.findall(key)[0], "%Y-%m-%d").date()
+
+
+def download_latest_dataset(bucket_dir: str) -> Tuple[pd.DataFrame, date]:
+    """All tranches under ``<bucket_dir>/datasets`` concatenated oldest -> newest, and the newest date."""
+    folder = os.path.join(bucket_dir, "datasets")
+    log.info(f"loading all available training data from {folder}")
+    try:
+        keys = [k for k in sorted(os.listdir(folder)) if _DATE_RE.search(k) and k.endswith(".csv")]
+        if not keys:
+            raise FileNotFoundError("no regression-dataset-*.csv tranche found")
+        dated = sorted(((k, _date_from_key(k)) for k in keys), key=lambda e: e[1])
+        dataset = pd.concat(pd.read_csv(os.path.join(folder, k)) for k, _ in dated)
+    except OSError as e:
+        log.error(e)
+        raise RuntimeError(f"failed to load training data from {folder}")
+    return dataset, dated[-1][1]
+
+
+def feature_columns(data: pd.DataFrame) -> List[str]:
+    """``['X']`` (the reference's schema) or ``['X0', 'X1', ...]``."""
+    if "X" in data.columns:
+        return ["X"]
+    cols = [c for c in data.columns if re.fullmatch(r"X\d+", str(c))]
+    if not cols:
+        raise RuntimeError("dataset has no feature column 'X' or 'X0..'")
+    return sorted(cols, key=lambda c: int(c[1:]))
+
+
+def split_mask(n: int, test_size: float = 0.2, seed: int = 42) -> np.ndarray:
+    """uint8 per row: 1 = train, 0 = test, 2 = unused -- the membership
+    ``train_test_split(X, y, test_size=0.2, random_state=42)`` (stage_1_train_model.py:98-103) draws:
+    ``perm = RandomState(seed).permutation(n)``; test = first ceil(test_size*n), train = next floor((1-test_size)*n)."""
+    n_test = int(np.ceil(test_size * n))
+    n_train = int(np.floor((1.0 - test_size) * n))
+    if n_train < 1 or n_test < 1:
+        raise ValueError(f"With n_samples={n}, test_size={test_size}, the resulting train set will be empty.")
+    perm = np.random.RandomState(seed).permutation(n)
+    mask = np.full(n, 2, dtype=np.uint8)
+    mask[perm[:n_test]] = 0
+    mask[perm[n_test:n_test + n_train]] = 1
+    return mask
+
+
+def metrics_from_stats(stats: np.ndarray) -> Tuple[float, float, float]:
+    """(MAPE, r_squared, max_residual) from the six device reductions (include/b2gram.h, b2_score)."""
+    sum_ape, sse, sy, syy, mx, cnt = (float(v) for v in stats)
+    if cnt < 1:
+        raise RuntimeError("no rows were scored")
+    mape = sum_ape / cnt
+    ss_tot = syy - sy * sy / cnt
+    if cnt < 2:
+        r2 = float("nan")  # sklearn: "R^2 score is not well-defined with less than two samples"
+    elif ss_tot > 0.0:
+        r2 = 1.0 - sse / ss_tot
+    else:
+        r2 = 1.0 if sse == 0.0 else 0.0
+    return mape, r2, mx
+
+
+def _metrics_record(mape: float, r_squared: float, max_residual: float) -> pd.DataFrame:
+    return pd.DataFrame({"date": [date.today()], "MAPE": [mape], "r_squared": [r_squared],
+                         "max_residual": [max_residual]})
+
+
+def model_metrics(y_actual, y_predicted) -> pd.DataFrame:
+    """Regression metrics record (stage_1_train_model.py:79-90), reduced on the GPU.
+
+    Scoring a one-column 'X = y_predicted' with coefficient 1 and intercept 0 reuses the fused
+    predict+metrics kernel, so the three reductions run in fp64 on the device."""
+    ctx = default_context()
+    y = np.ascontiguousarray(np.asarray(y_actual, dtype=np.float64).ravel(), dtype=np.float32)
+    p = np.ascontiguousarray(np.asarray(y_predicted, dtype=np.float64).reshape(-1, 1), dtype=np.float32)
+    _, stats = ctx.score(p, np.ones(1), 0.0, y=y, want_yhat=False)
+    return _metrics_record(*metrics_from_stats(stats))
+
+
+def train_model(data: pd.DataFrame):
+    """Train the regression model and compute hold-out metrics (stage_1_train_model.py:93-108).
+
+    Returns ``(sklearn LinearRegression, one-row metrics DataFrame)`` like the reference."""
+    cols = feature_columns(data)
+    X = np.ascontiguousarray(data[cols].to_numpy(dtype=np.float32))
+    y = np.ascontiguousarray(data["y"].to_numpy(dtype=np.float32))
+    n = X.shape[0]
+    mask = split_mask(n)
+
+    ctx = default_context()
+    Xd, yd, md = ctx.to_device(X), ctx.to_device(y), ctx.to_device(mask)
+    try:
+        reg = B200LinearRegression(fit_intercept=True, ctx=ctx)
+        reg.fit(Xd, yd, row_mask=md, mask_keep=1)
+        _, stats = ctx.score(Xd, reg.coef_, float(reg.intercept_), y=yd, row_mask=md, mask_keep=0,
+                             want_yhat=False)
+    finally:
+        Xd.free(); yd.free(); md.free()
+    return reg.to_sklearn(), _metrics_record(*metrics_from_stats(stats))
+
+
+def persist_model(model, data_date: date, bucket_dir: str) -> None:
+    """joblib-dump the estimator as ``regressor-<date>.joblib`` (stage_1_train_model.py:113-114) and
+    place it under ``<bucket_dir>/models/`` (the S3 upload of :117-121)."""
+    model_filename = f"regressor-{data_date}.joblib"
+    dump(model, model_filename)
+    try:
+        os.makedirs(os.path.join(bucket_dir, "models"), exist_ok=True)
+        shutil.move(model_filename, os.path.join(bucket_dir, "models", model_filename))
+        log.info(f"stored {model_filename} under {bucket_dir}/models/")
+    except OSError as e:
+        log.error(e)
+        raise RuntimeError("could not store model - check the bucket directory")
+
+
+def persist_metrics(metrics: pd.DataFrame, data_date: date, bucket_dir: str) -> None:
+    """``regressor-<date>.csv`` with header ``date,MAPE,r_squared,max_residual`` (:130-131)."""
+    metrics_filename = f"regressor-{data_date}.csv"
+    metrics.to_csv(metrics_filename, header=True, index=False)
+    try:
+        os.makedirs(os.path.join(bucket_dir, "model-metrics"), exist_ok=True)
+        shutil.move(metrics_filename, os.path.join(bucket_dir, "model-metrics", metrics_filename))
+        log.info(f"stored {metrics_filename} under {bucket_dir}/model-metrics/")
+    except OSError as e:
+        log.error(e)
+        raise RuntimeError("could not store model metrics - check the bucket directory")
+
+
+def configure_logger() -> logging.Logger:
+    """stdout logger with the reference's record format (stage_1_train_model.py:145-158)."""
+    handler = logging.StreamHandler(sys.stdout)
+    handler.setFormatter(logging.Formatter(
+        "%(asctime)s - %(levelname)s - %(module)s.%(funcName)s - %(message)s"))
+    logger = logging.getLogger(__name__)
+    logger.addHandler(handler)
+    logger.setLevel(logging.INFO)
+    return logger
+
+
+def run() -> int:
+    """``__main__`` body: exit status 0 on success, 1 on any failure (stage_1_train_model.py:170-178).
+    Sentry is initialised only when SENTRY_DSN is set and sentry_sdk is importable (the reference makes it
+    mandatory; the drop-in must also run where no DSN secret is mounted)."""
+    dsn = os.environ.get("SENTRY_DSN")
+    if dsn:
+        try:
+            import sentry_sdk
+            sentry_sdk.init(dsn, traces_sample_rate=1.0)
+            sentry_sdk.set_tag("stage", "stage-1-train-model")
+        except ImportError:
+            pass
+    global log
+    log = configure_logger()
+    try:
+        main()
+    except Exception as e:  # noqa: BLE001 - mirror of the reference's catch-all
+        log.error(e)
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(run())

@@ -1,0 +1,149 @@
+/*
+ * b2gram.h -- C-ABI of libb2gram.so: the B200 (sm_100a) retrain hot path of
+ * AlexIoannides/bodywork-mlops-demo, i.e. the least-squares / ridge fit that
+ * mlops_simulation/stage_1_train_model.py performs through scikit-learn.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The reference is pure Python, so the binding a maintainer adds is a ctypes stub
+ * (see INTEGRATION.md); every entry point cites the reference call it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (B2_E_*); text via b2_last_error()
+ *     (thread-local).  No exceptions cross the boundary.
+ *   - the caller owns every buffer it passes; b2_ctx owns device scratch, streams, the
+ *     fp64 sufficient statistic S and (optionally) one NCCL communicator.
+ *   - one b2_ctx == one GPU; one process per GPU for multi-GPU (rows shard by rank, the
+ *     only exchange is b2_gram_allreduce).  A ctx is not re-entrant.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *     fails with B2_E_CUDA.
+ *
+ * Sufficient statistic.  S = [X 1 y]^T [X 1 y], (D+2) x (D+2), row-major fp64, index
+ * order: features 0..D-1, the ones column (D), y (D+1).  S[D][D] is the row count.
+ */
+#ifndef B2GRAM_H_
+#define B2GRAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+#define B2_MAX_D 128
+
+/* element type of X */
+#define B2_F32 0
+#define B2_BF16 1
+
+/* where a caller buffer lives */
+#define B2_MEM_DEVICE 0 /* device pointer (HBM)                                   */
+#define B2_MEM_HOST 1   /* host pointer (pinned preferred); streamed in row blocks */
+
+/* kernel selection for b2_gram_accumulate */
+#define B2_KERNEL_AUTO 0   /* tcgen05 path when shape/alignment allow, else CUDA-core */
+#define B2_KERNEL_SIMT 1   /* fp64-accumulating CUDA-core kernel (any D <= 128)       */
+#define B2_KERNEL_TCGEN05 2 /* TMA -> smem -> bf16 hi/lo split -> tcgen05.mma -> TMEM   */
+
+/* error codes */
+#define B2_OK 0
+#define B2_E_ARG (-1)
+#define B2_E_CUDA (-2)
+#define B2_E_STATE (-3)
+#define B2_E_SINGULAR (-4) /* Cholesky met a non-positive pivot (rank-deficient, alpha == 0) */
+#define B2_E_NCCL (-5)
+#define B2_E_UNSUPPORTED (-6)
+
+typedef struct b2_ctx b2_ctx;
+
+/* ---- library / context ------------------------------------------------------------ */
+int b2_abi_version(void);
+const char* b2_last_error(void);
+int b2_device_count(int* n_out);
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+int b2_ctx_sync(b2_ctx* ctx);
+/* name, SM count, HBM bytes of the ctx's device (name_cap bytes incl. NUL) */
+int b2_ctx_info(b2_ctx* ctx, char* name, int name_cap, int* sm_count, size_t* hbm_bytes);
+/* force a kernel family (B2_KERNEL_*); default AUTO */
+int b2_ctx_set_kernel(b2_ctx* ctx, int kernel);
+/* rows of fp32 tensor-core accumulation before a TMEM drain into fp64 (default 8192) */
+int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows);
+
+/* ---- caller-owned buffers (helpers; the Python shim has no other CUDA binding) ------------ */
+int b2_dev_alloc(b2_ctx* ctx, size_t bytes, void** out);
+int b2_dev_free(b2_ctx* ctx, void* p);
+int b2_host_alloc(b2_ctx* ctx, size_t bytes, void** out); /* pinned */
+int b2_host_free(b2_ctx* ctx, void* p);
+int b2_copy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
+int b2_copy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
+int b2_dev_memset(b2_ctx* ctx, void* dst, int value, size_t bytes);
+
+/* ---- Gram accumulation: replaces LinearRegression.fit's pass over the rows -----------------
+ * reference: stage_1_train_model.py:105-106 -> sklearn/linear_model/_base.py (centre + gelsd). */
+int b2_gram_reset(b2_ctx* ctx, int d);
+/* S += [X 1 y]^T [X 1 y] over the rows of this block (this rank's shard).
+ *   X        n_rows x d, row-major, leading dimension ldx (elements), dtype x_dtype
+ *   y        n_rows fp32
+ *   row_mask NULL, or one byte per row: a row is used iff row_mask[r] == mask_keep.
+ *            (lets train_test_split's shuffled 80/20 membership -- stage_1_train_model.py:98-103 --
+ *            be applied without gathering rows)
+ *   mem_kind where X / y / row_mask live (all three the same)                                */
+int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_rows,
+                       int d, int64_t ldx, int mem_kind, const uint8_t* row_mask, int mask_keep);
+/* sum S over the ranks of the communicator (one ncclAllReduce of (d+2)^2 doubles) */
+int b2_gram_allreduce(b2_ctx* ctx);
+/* copy S out / in (incremental-refit state).  S_out/S_in: (d+2)^2 doubles on the host */
+int b2_gram_export(b2_ctx* ctx, double* S_out, int64_t* n_rows_out);
+int b2_gram_import(b2_ctx* ctx, const double* S_in, int d);
+
+/* ---- solve: replaces scipy.linalg.lstsq + _set_intercept ----------------------------------------
+ * reference: sklearn/linear_model/_base.py (lstsq on centred data; intercept_ = y_mean - x_mean.coef_)
+ * Single-SM fp64 Cholesky of (Xc^T Xc + alpha I).  coef: d doubles, intercept: 1 double (host).
+ * fit_intercept = 0 solves the uncentred problem.  Returns B2_E_SINGULAR on a non-positive pivot. */
+int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double* intercept);
+/* eigenvalues of the centred Gram (device Jacobi) -> singular_ (descending, d doubles) and rank_
+ * (count of singular values > cond * max), plus the minimum-norm coefficients gelsd would return.
+ * Any output pointer may be NULL. */
+int b2_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept, double* coef, double* intercept,
+                      double* singular, int* rank);
+
+/* ---- scoring: replaces model.predict and model_metrics ------------------------------------------
+ * reference: stage_1_train_model.py:107 / stage_2_serve_model.py:78 (X @ coef_ + intercept_)
+ *            stage_1_train_model.py:79-90 (MAPE, r2_score, max_error)
+ * yhat may be NULL (metrics only); y may be NULL (predict only; stats_out untouched).
+ * stats_out (host, 6 doubles): [ sum |yhat-y|/max(|y|,eps_f64), sum (y-yhat)^2, sum y, sum y^2,
+ *                               max |y-yhat|, rows used ]
+ * With a communicator, b2_score_allreduce combines the six across ranks (sum x5 / max x1). */
+int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int64_t ldx,
+             int mem_kind, const double* coef, double intercept, const float* y,
+             const uint8_t* row_mask, int mask_keep, float* yhat, double* stats_out);
+int b2_score_allreduce(b2_ctx* ctx, double* stats_inout);
+
+/* ---- synthetic rows on the device (benchmarks): stage_3_synthetic_data_generation.py:36-43 --------
+ * X_ij ~ U(0,100), eps ~ N(0,1), y = alpha + beta * sum_j X_ij + sigma * eps   (Philox4x32-10,
+ * counter = global row index + row_offset, so shards of one dataset can be drawn independently). */
+int b2_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n_rows, int d, int64_t ldx,
+             int x_dtype, double alpha, double beta, double sigma, void* X_dev, float* y_dev);
+
+/* ---- multi-GPU (one process per GPU; NCCL is dlopen'ed on first use) ------------------------------ */
+int b2_comm_unique_id(char* id_out /* 128 bytes */);
+int b2_comm_init(b2_ctx* ctx, int n_ranks, int rank, const char* id /* 128 bytes */);
+int b2_comm_destroy(b2_ctx* ctx);
+int b2_comm_barrier(b2_ctx* ctx);
+
+/* ---- timing (CUDA events on the ctx stream) ---------------------------------------------------------
+ * b2_timer_start/stop bracket any sequence of calls; *_ms is device time between the two events.
+ * b2_last_kernel_ms: device time of the dominant Gram kernel launches inside the most recent
+ * b2_gram_accumulate (sum over its launches), and how many kernels that call launched. */
+int b2_timer_start(b2_ctx* ctx);
+int b2_timer_stop(b2_ctx* ctx, double* ms_out);
+int b2_last_kernel_ms(b2_ctx* ctx, double* gram_ms_out, int* launches_out);
+/* total number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int b2_launch_count(b2_ctx* ctx, int64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2GRAM_H_ */

@@ -1,0 +1,133 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b2gram.h declares,
+fails loudly without a GPU, and the host logic (split mask, metrics algebra, artefact layout) matches
+the oracle.  No compute call is made here."""
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bodywork_mlops_demo_b200 as b2
+from bodywork_mlops_demo_b200 import stage_1_train_model as s1
+from oracle import ols_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "b2gram.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(b2.native.lib_path())
+    declared = _header_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b2gram.h but not exported"
+    # and the Python binding table covers the header one to one
+    assert sorted(b2.native.EXPORTED_SYMBOLS) == declared
+
+
+def test_abi_version_and_error_string():
+    lib = b2.native.load()
+    assert lib.b2_abi_version() == 1
+    assert isinstance(b2.native.last_error(), str)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if b2.native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        b2.Context(0)
+    with pytest.raises(RuntimeError):
+        s1.model_metrics(np.ones(4), np.ones(4))
+
+
+def test_library_has_blackwell_native_sass():
+    """tcgen05 / TMA must be in the shipped binary (B200_PROFILING.md: UTC*MMA, UTMALDG, LDTM)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", b2.native.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.parametrize("n", [5, 57, 1440, 10_001])
+def test_split_mask_equals_reference_split(golden_dir, n):
+    g = np.load(os.path.join(golden_dir, f"sk_split_n{n}.npz"))
+    mask = s1.split_mask(n)
+    assert np.array_equal(np.sort(np.flatnonzero(mask == 1)), np.sort(g["train"]))
+    assert np.array_equal(np.sort(np.flatnonzero(mask == 0)), np.sort(g["test"]))
+    tr, te = orc.split_indices(n)
+    assert set(np.flatnonzero(mask == 1)) == set(tr) and set(np.flatnonzero(mask == 0)) == set(te)
+
+
+def test_metrics_from_stats_matches_reference_metrics(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_model_metrics.npz"))
+    stats = orc.score_stats(g["y"], g["p"])
+    mape, r2, mx = s1.metrics_from_stats(stats)
+    assert mape == pytest.approx(float(g["MAPE"]), rel=1e-12)
+    assert r2 == pytest.approx(float(g["r_squared"]), rel=1e-10)
+    assert mx == pytest.approx(float(g["max_residual"]), rel=1e-14)
+
+
+def test_metrics_edge_cases():
+    # constant y, perfect prediction -> r2 == 1 (sklearn force_finite); imperfect -> 0
+    y = np.full(10, 3.0)
+    assert s1.metrics_from_stats(orc.score_stats(y, y))[1] == 1.0
+    assert s1.metrics_from_stats(orc.score_stats(y, y + 1))[1] == 0.0
+    with pytest.raises(RuntimeError):
+        s1.metrics_from_stats(np.zeros(6))
+
+
+def test_bf16_bit_conversion_round_to_nearest_even():
+    x = np.array([1.0, 1.00390625, 1.01171875, -3.14159, 0.0, 65504.0, 1e-20], dtype=np.float32)
+    bits = b2.native.to_bf16_bits(x)
+    back = b2.native.from_bf16_bits(bits)
+    assert back[0] == 1.0 and back[4] == 0.0
+    assert np.all(np.abs(back - x) <= np.abs(x) * 2.0 ** -8)
+    assert back[1] == 1.0            # 1 + 2^-8 ties to even (down)
+    assert back[2] == np.float32(1.015625)  # 1 + 3*2^-8 ties to even (up)
+
+
+def test_sklearn_artefact_layout_and_stage2_contract(tmp_path):
+    """The estimator we dump must behave exactly like the reference's for stage_2_serve_model.py:65,78,79."""
+    import joblib
+    from sklearn.linear_model import LinearRegression
+    est = b2.B200LinearRegression()
+    est.coef_ = np.array([0.5, -0.25]); est.intercept_ = np.float64(1.5)
+    est.rank_ = 2; est.singular_ = np.array([3.0, 1.0]); est.n_features_in_ = 2
+    reg = est.to_sklearn()
+    assert type(reg) is LinearRegression and str(reg) == "LinearRegression()"
+    path = tmp_path / "regressor-2021-04-08.joblib"
+    joblib.dump(reg, path)
+    loaded = joblib.load(io.BytesIO(path.read_bytes()))
+    X = np.array([[50.0, 2.0]], ndmin=2)
+    assert loaded.predict(X)[0] == pytest.approx(0.5 * 50 - 0.25 * 2 + 1.5)
+    ref = LinearRegression().fit(np.random.RandomState(0).rand(20, 2), np.random.RandomState(1).rand(20))
+    assert set(vars(ref)) == set(vars(loaded))  # same attribute set as a genuinely fitted estimator
+    assert loaded.coef_.dtype == np.float64 and loaded.coef_.shape == (2,)
+
+
+def test_feature_columns_and_dataset_loader(tmp_path):
+    import pandas as pd
+    folder = tmp_path / "datasets"
+    folder.mkdir()
+    for day, n in (("2021-04-09", 3), ("2021-04-08", 2)):
+        pd.DataFrame({"date": [day] * n, "y": np.arange(n, dtype=float), "X": np.arange(n, dtype=float)}) \
+            .to_csv(folder / f"regression-dataset-{day}.csv", index=False)
+    data, newest = s1.download_latest_dataset(str(tmp_path))
+    assert str(newest) == "2021-04-09" and len(data) == 5
+    assert list(data["date"])[:2] == ["2021-04-08"] * 2   # oldest tranche first
+    assert s1.feature_columns(data) == ["X"]
+    assert s1.feature_columns(pd.DataFrame({"y": [1], "X10": [1], "X2": [1]})) == ["X2", "X10"]
+    with pytest.raises(RuntimeError):
+        s1.download_latest_dataset(str(tmp_path / "missing"))
