@@ -190,7 +190,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->S), sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_part), sizeof(double) * (size_t)ctx->sm_count * kTcAccElems));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_side), sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
-  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_red), sizeof(double) * (kTcAccElems + 2 * kMaxD + 8)));
+  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_red), sizeof(double) * (kTcAccElems + 16)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->shift), sizeof(float) * 64 * (kMaxD + 1)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->simt_part), sizeof(double) * (size_t)ctx->simt_ctas * kMaxS * kMaxS));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->score_part), sizeof(double) * ((size_t)ctx->score_ctas + 1) * 6));
@@ -530,7 +530,7 @@ int b2_comm_barrier(b2_ctx* ctx) {
   if (ctx->n_ranks == 1 || ctx->comm == nullptr) return b2_ctx_sync(ctx);
   NcclApi* api = nccl();
   if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
-  double* slot = ctx->tc_red + kTcAccElems + 2 * kMaxD + 4;  // spare scratch
+  double* slot = ctx->tc_red + kTcAccElems + 8;  // spare scratch
   B2_NCCL(api, api->AllReduce(slot, slot, 1, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   return B2_OK;

@@ -15,12 +15,12 @@ constexpr int kMaxS = kMaxD + 2;         // 130: features, ones, y
 constexpr int kKernelEventPairs = 64;
 
 // ---- tcgen05 Gram kernel geometry (gram_tc.cu) ------------------------------------------
-constexpr int kTcRows = 32;              // rows of X per pipeline stage (MMA K = 2 x 16)
+constexpr int kTcRows = 64;              // rows of X per pipeline stage (4 MMA K-steps of 16)
 constexpr int kTcM = 128;                // MMA M: feature index (zero padded)
-constexpr int kTcN = 256;                // MMA N: [hi | lo] feature index
-constexpr int kTcAccElems = kTcM * kTcN; // fp32 accumulators drained per chunk
-constexpr int kTcXformWarps = 8;
-constexpr int kTcSideDoubles = kTcXformWarps * 32 * 2 + 8;  // per-CTA side sums (s1,sxy per thread) + y sums
+constexpr int kTcN = 144;                // MMA N: 128 feature columns (hi) + 16 extra columns [1, y_hi, y_lo, 0...]
+constexpr int kTcAccCols = 2 * kTcN;     // two accumulators: A = hi and A = lo against the same B = [hi | E]
+constexpr int kTcAccElems = kTcM * kTcAccCols;  // fp32 accumulators drained per chunk (36 864)
+constexpr int kTcSideDoubles = 8;        // per-CTA CUDA-core sums: sum y', sum y'^2, rows used
 
 void set_error(const char* fmt, ...);
 
@@ -57,7 +57,7 @@ struct b2_ctx {
   // tcgen05 path scratch
   double* tc_part = nullptr;           // [sm_count][kTcAccElems]   per-CTA fp64 partial Gram (col-major)
   double* tc_side = nullptr;           // [sm_count][kTcSideDoubles]
-  double* tc_red = nullptr;            // [kTcAccElems + 2*kMaxD + 8] reduced over CTAs
+  double* tc_red = nullptr;            // [kTcAccElems + 8] reduced over CTAs
   float* shift = nullptr;              // [64][kMaxD + 1] partial sums of the row sample -> per-column shift c
   bool tc_attr_set = false;
   // SIMT path scratch

@@ -3,26 +3,27 @@
 // Replaces the pass over the training rows inside LinearRegression.fit
 // (stage_1_train_model.py:105-106 -> sklearn/linear_model/_base.py: centre + LAPACK gelsd).
 //
-// Data flow per CTA (persistent, one CTA per SM, contiguous range of 32-row tiles):
+// Data flow per CTA (persistent, one CTA per SM, contiguous range of 64-row tiles):
 //
-//   HBM --TMA(cp.async.bulk.tensor)--> smem raw tile [32 rows][D] (+ y, + row mask)
-//       --transform warps: v = x - c (per-column shift), bf16 split v = hi + lo,
-//         CUDA-core side sums  sum v, sum v*y', sum y', sum y'^2, row count  (fp32 -> fp64)
-//       --> smem operand tile, K-major canonical layout (8x16B core matrices, no swizzle)
-//       --tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M=128 N=256 K=16:
-//             D[i][j]      += sum_r hi[r][i] * hi[r][j]        (columns   0..127)
-//             D[i][128+j]  += sum_r hi[r][i] * lo[r][j]        (columns 128..255)
-//         accumulators live in TMEM (2 x 256 columns, double buffered)
-//       --every `drain_rows` rows: epilogue warps tcgen05.ld the 128x256 fp32 block and fold it
-//         into this CTA's fp64 partial in global memory (L2 resident).
+//   HBM --TMA (cp.async.bulk.tensor, evict-first)--> smem raw tile [64 rows][D] (+ y, + row mask)
+//     --16 transform warps: v = x - c (per-column shift), bf16 split v = hi + lo
+//     -- 1 "E" warp: extra columns E = [1, y'_hi, y'_lo] (y' = y - c_y), CUDA-core sums of y', y'^2, rows
+//     --> smem operand tile, K-major canonical layout (8 x 16 B core matrices, no swizzle):
+//            rows j = 0..127 hi | 128..143 E | 144..271 lo        (one 16-byte chunk = 8 consecutive rows of X)
+//     --tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128, N=144, K=16, two per K-step:
+//            D1[i][j] += sum_r hi[r][i] * [hi | E][r][j]      TMEM columns   0..143
+//            D2[i][j] += sum_r lo[r][i] * [hi | E][r][j]      TMEM columns 256..399
+//        so D1[:, :128] = hi^T hi, D2[:, :128] = lo^T hi, column 128 = sum v, columns 129/130 = sum v*y'.
+//     --every `drain_rows` rows: epilogue warps tcgen05.ld both accumulators and fold them into this
+//        CTA's fp64 partial in global memory (L2 resident).
 //
-// Why the shift and the split: the tensor core accumulates fp32 with truncation, so raw
-// (uncentred) second moments cannot reach the 1e-4 coefficient tolerance; after the shift the
-// Gram is ~diagonal and the centring in the solve subtracts almost nothing.  hi+lo carries
-// 16 mantissa bits, i.e. products are accurate to ~2^-17 relative (lo*lo is dropped).
+// Why the shift and the split: the tensor core accumulates fp32 with truncation, so raw (uncentred)
+// second moments cannot reach the 1e-4 coefficient tolerance; after the shift the Gram is ~diagonal and
+// the centring in the solve subtracts almost nothing.  hi+lo carries 16 mantissa bits, i.e. products are
+// accurate to ~2^-17 relative (lo*lo is dropped).
 //
-// The finalize kernels reduce the per-CTA partials in a fixed order (deterministic), undo the
-// shift in fp64 and add the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
+// The finalize kernels reduce the per-CTA partials in a fixed order (deterministic), undo the shift in
+// fp64 and add the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
 #include <cuda_bf16.h>
 
 #include "b2_internal.cuh"
@@ -33,24 +34,32 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------
-constexpr int kRawStages = 5;
-constexpr int kOpStages = 3;
-constexpr int kThreads = 512;           // 16 warps: 0 TMA, 1 MMA(+TMEM alloc), 2-3 idle, 4-7 epilogue, 8-15 transform
-constexpr uint32_t kRawStageBytes = 16384;  // 32 rows x 128 fp32 (max)
-constexpr uint32_t kOpLBO = 4096;       // bytes between the 8-row K groups (core matrices along K)
-constexpr uint32_t kOpSBO = 128;        // bytes between 8-feature groups (core matrices along M/N)
-constexpr uint32_t kOpStageBytes = (kTcRows / 8) * kOpLBO;  // 16384: [4 kgroups][256 j][8 k] bf16
+constexpr int kRawStages = 4;
+constexpr int kOpStages = 2;
+constexpr int kXformWarps = 16;
+constexpr int kThreads = 32 * (8 + kXformWarps);  // warps: 0 TMA, 1 MMA(+TMEM alloc), 2 E, 3 idle, 4-7 epilogue, 8.. transform
+constexpr int kProducers = kXformWarps + 1;        // warps that fill an operand stage (transform + E)
+constexpr int kKGroups = kTcRows / 8;              // 8-row K groups per stage
+constexpr uint32_t kRawStageBytes = kTcRows * kMaxD * 4;      // 32768 (fp32, D = 128)
+constexpr uint32_t kGroupsPerK = 16 + 2 + 16;                 // hi | E | lo groups of 8 j-rows
+constexpr uint32_t kOpSBO = 128;                              // bytes between 8-row j groups (core matrices along M/N)
+constexpr uint32_t kOpLBO = kGroupsPerK * kOpSBO;             // 4352: bytes between K groups (core matrices along K)
+constexpr uint32_t kOpEOff = 16 * kOpSBO;                     // E block inside a K group
+constexpr uint32_t kOpLoOff = 18 * kOpSBO;                    // lo block inside a K group
+constexpr uint32_t kOpStageBytes = kKGroups * kOpLBO;         // 34816
 constexpr uint32_t kOffRaw = 0;
-constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;          // 81920
-constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;              // 131072
-constexpr uint32_t kOffMask = kOffY + kRawStages * 128;                     // 131712
-constexpr uint32_t kOffBar = kOffMask + kRawStages * 128;                   // 132352
-constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 4;                // 20
-constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;                    // 132512
-constexpr uint32_t kOffShift = kOffTmemPtr + 16;                            // 132528
-constexpr uint32_t kSmemBytes = kOffShift + (kMaxD + 4) * 4 + 1024;         // + alignment slack
+constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;     // 131072
+constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;         // 200704
+constexpr uint32_t kOffMask = kOffY + kRawStages * 256;
+constexpr uint32_t kOffBar = kOffMask + kRawStages * 128;
+constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 2;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kOffShift = kOffTmemPtr + 16;
+constexpr uint32_t kSmemBytes = kOffShift + (kMaxD + 4) * 4 + 1024;    // + alignment slack (~204 KB)
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kTmemD2Col = 256;                                   // second accumulator's first column
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=144, M=128 (cute::UMMA::InstrDescriptor layout)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
                             ((uint32_t)(kTcM >> 4) << 24);
 
@@ -69,24 +78,29 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug must end in a trap (clean launch failure), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait with a hardware suspend hint (the thread sleeps inside try_wait and is woken by the arrive, so
+// waiting warps do not burn issue slots).  Bounded: a protocol bug must end in a trap (a clean launch
+// failure), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
+  uint64_t t0 = 0;
+  while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (!done && spin > (1u << 24)) {
-      if (err != nullptr) {
-        *reinterpret_cast<volatile int*>(err) = code | (blockIdx.x << 8);
-        __threadfence_system();
-      }
-      __trap();
-    }
+    if (done) break;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -131,15 +145,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -149,14 +160,46 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint32_t (&v)[
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                : "memory");
 }
-
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// one element of the raw tile as fp32 (T = float: 4-byte load; T = bf16: 2-byte load, widen)
 template <typename T>
-__device__ __forceinline__ float raw_ld(const T* p);
+__device__ __forceinline__ float raw_ld_shared(uint32_t addr);
 template <>
-__device__ __forceinline__ float raw_ld<float>(const float* p) { return *p; }
+__device__ __forceinline__ float raw_ld_shared<float>(uint32_t addr) { return ld_shared_f32(addr); }
 template <>
-__device__ __forceinline__ float raw_ld<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __uint_as_float(((uint32_t) * reinterpret_cast<const unsigned short*>(p)) << 16);
+__device__ __forceinline__ float raw_ld_shared<__nv_bfloat16>(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  return __uint_as_float(((uint32_t)h) << 16);
+}
+template <typename T>
+__device__ __forceinline__ float raw_ld_global(const T* p);
+template <>
+__device__ __forceinline__ float raw_ld_global<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float raw_ld_global<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+// bf16 split of two fp32 values: hi = rn(v), lo = rn(v - hi), packed (element 0 in the low half)
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -191,7 +234,7 @@ __global__ void tc_shift_kernel(const T* __restrict__ X, const float* __restrict
 #pragma unroll 8
   for (int64_t s = s0; s < s1; ++s) {
     const int64_t row = s * stride;
-    acc += (j < d) ? raw_ld<T>(X + row * ldx + j) : __ldg(y + row);
+    acc += (j < d) ? raw_ld_global<T>(X + row * ldx + j) : __ldg(y + row);
   }
   sp[blockIdx.x * kShiftStride + (j == d ? kMaxD : j)] = acc;
 }
@@ -204,10 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
                int64_t n_rows, int d, const float* __restrict__ shift, int chunk_tiles,
-               double* __restrict__ part, double* __restrict__ side, int* err) {
+               double* __restrict__ part, double* __restrict__ side) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -215,8 +258,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t bar_raw_empty = bar_raw_full + 8 * kRawStages;        // [kRawStages]
   const uint32_t bar_op_full = bar_raw_empty + 8 * kRawStages;         // [kOpStages]
   const uint32_t bar_op_empty = bar_op_full + 8 * kOpStages;           // [kOpStages]
-  const uint32_t bar_acc_full = bar_op_empty + 8 * kOpStages;          // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;                    // [2]
+  const uint32_t bar_acc_full = bar_op_empty + 8 * kOpStages;          // [1]
+  const uint32_t bar_acc_empty = bar_acc_full + 8;                     // [1]
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* shift_s = reinterpret_cast<float*>(smem + kOffShift);
 
@@ -231,16 +274,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRawStages; ++s) {
       mbar_init(bar_raw_full + 8 * s, 1);
-      mbar_init(bar_raw_empty + 8 * s, kTcXformWarps);
+      mbar_init(bar_raw_empty + 8 * s, kProducers);
     }
     for (int s = 0; s < kOpStages; ++s) {
-      mbar_init(bar_op_full + 8 * s, kTcXformWarps);
+      mbar_init(bar_op_full + 8 * s, kProducers);
       mbar_init(bar_op_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, 4);
-    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -248,12 +289,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmY);
     if (has_mask) tma_prefetch_desc(&tmM);
   }
-  if (warp == 1) {  // TMEM: all 512 columns (two 128x256 fp32 accumulators)
+  if (warp == 1) {  // TMEM: 512 columns (accumulators at 0..143 and 256..399)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + kOffTmemPtr)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // zero the operand stages once: feature columns >= d are never written and must read as 0
+  // zero the operand stages once: feature rows >= d, the unused E rows and the lo/hi padding read as 0
   for (uint32_t o = threadIdx.x * 16; o < kOpStages * kOpStageBytes; o += kThreads * 16)
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
   for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
@@ -268,148 +309,170 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t x_bytes = (uint32_t)(kTcRows * d * sizeof(T));
-      const uint32_t tx = x_bytes + kTcRows * 4 + (has_mask ? kTcRows : 0);
+      const uint32_t tx = (uint32_t)(kTcRows * d * sizeof(T)) + kTcRows * 4 + (has_mask ? kTcRows : 0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % kRawStages;
-        const uint32_t ph = (it / kRawStages) & 1;
-        mbar_wait(bar_raw_empty + 8 * s, ph ^ 1, err, 1);
+        mbar_wait(bar_raw_empty + 8 * s, ph ^ 1);
         const uint32_t full = bar_raw_full + 8 * s;
         mbar_expect_tx(full, tx);
         const int64_t row0 = (tile_begin + it) * kTcRows;
         tma_load_2d(sbase + kOffRaw + s * kRawStageBytes, &tmX, 0, (int)row0, full);
-        if (y_map_2d) tma_load_2d(sbase + kOffY + s * 128, &tmY, 0, (int)(row0 >> 2), full);
-        else tma_load_1d(sbase + kOffY + s * 128, &tmY, (int)row0, full);
+        if (y_map_2d) tma_load_2d(sbase + kOffY + s * 256, &tmY, 0, (int)(row0 >> 2), full);
+        else tma_load_1d(sbase + kOffY + s * 256, &tmY, (int)row0, full);
         if (has_mask) tma_load_1d(sbase + kOffMask + s * 128, &tmM, (int)row0, full);
+        if (++s == kRawStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
+      int os = 0;
+      uint32_t oph = 0;
+      int in_chunk = 0, chunk = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int os = it % kOpStages;
-        const uint32_t oph = (it / kOpStages) & 1;
-        const int chunk = it / chunk_tiles;
-        const int in_chunk = it - chunk * chunk_tiles;
-        const int b = chunk & 1;
-        if (in_chunk == 0) {  // first tile of a chunk: the TMEM buffer must have been drained
-          mbar_wait(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1, err, 2);
+        if (in_chunk == 0) {  // the single TMEM accumulator pair must have been drained
+          mbar_wait(bar_acc_empty, (chunk & 1) ^ 1);
           tc_fence_after();
         }
-        mbar_wait(bar_op_full + 8 * os, oph, err, 3);
+        mbar_wait(bar_op_full + 8 * os, oph);
         tc_fence_after();
         const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes;
-        const uint32_t tmem_d = tmem_base + (uint32_t)(b * kTcN);
 #pragma unroll
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint64_t desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO);
-          umma_bf16(tmem_d, desc, desc, (in_chunk > 0 || k2 > 0) ? 1u : 0u);
+          const uint64_t b_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO);               // [hi | E], also A = hi
+          const uint64_t lo_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO + kOpLoOff);   // A = lo
+          const uint32_t acc = (in_chunk > 0 || k2 > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, b_desc, b_desc, acc);
+          umma_bf16(tmem_base + kTmemD2Col, lo_desc, b_desc, acc);
         }
         umma_commit(bar_op_empty + 8 * os);  // frees the operand stage when these MMAs retire
-        if (in_chunk == chunk_tiles - 1 || it == my_tiles - 1) umma_commit(bar_acc_full + 8 * b);
+        const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
+        if (last) { umma_commit(bar_acc_full); in_chunk = 0; ++chunk; }
+        else ++in_chunk;
+        if (++os == kOpStages) { os = 0; oph ^= 1; }
       }
+    }
+  } else if (warp == 2) {
+    // ===== E warp: extra operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' =====
+    const float c_y = shift_s[kMaxD];
+    double sy = 0.0, syy = 0.0, cnt = 0.0;
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      mbar_wait(bar_raw_full + 8 * rs, rph);
+      mbar_wait(bar_op_empty + 8 * os, oph ^ 1);
+      tc_fence_after();
+      const int64_t row0 = (tile_begin + it) * kTcRows;
+      const uint32_t y_addr = sbase + kOffY + rs * 256;
+      const uint32_t m_addr = sbase + kOffMask + rs * 128;
+      const uint32_t e_addr = sbase + kOffOp + os * kOpStageBytes + kOpEOff;
+      float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+      for (int h = 0; h < kTcRows / 32; ++h) {
+        const int rr = lane + 32 * h;
+        bool use = (row0 + rr) < n_rows;
+        if (use && has_mask) use = (ld_shared_u8(m_addr + rr) == (uint32_t)keep);
+        const float yv = use ? ld_shared_f32(y_addr + rr * 4) - c_y : 0.f;
+        uint32_t yh, yl;
+        split2(yv, 0.f, yh, yl);
+        const uint32_t dst = e_addr + (rr >> 3) * kOpLBO + (rr & 7) * 2;
+        st_shared_u16(dst, use ? 0x3F80u : 0u);   // bf16(1.0)
+        st_shared_u16(dst + 16, yh);
+        st_shared_u16(dst + 32, yl);
+        a += yv;
+        b = fmaf(yv, yv, b);
+        c += use ? 1.f : 0.f;
+      }
+      sy += (double)a; syy += (double)b; cnt += (double)c;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_op_full + 8 * os);
+        mbar_arrive(bar_raw_empty + 8 * rs);
+      }
+      if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+      if (++os == kOpStages) { os = 0; oph ^= 1; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+      double* ys = side + (size_t)blockIdx.x * kTcSideDoubles;
+      ys[0] = sy; ys[1] = syy; ys[2] = cnt;
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue: TMEM -> registers -> fp64 partial in global (column-major [col][feature]) =====
     const int w = warp & 3;  // TMEM lane quadrant this warp may access
     double* my_part = part + (size_t)blockIdx.x * kTcAccElems + w * 32 + lane;
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      const int b = chunk & 1;
-      mbar_wait(bar_acc_full + 8 * b, (chunk >> 1) & 1, err, 4);
+      mbar_wait(bar_acc_full, chunk & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(b * kTcN);
 #pragma unroll 1
-      for (int p = 0; p < kTcN / 32; ++p) {
-        uint32_t r[32];
-        tmem_ld32(taddr + p * 32, r);
+      for (int p = 0; p < kTcAccCols / 16; ++p) {
+        const int acc_sel = p / (kTcN / 16);          // 0: A = hi, 1: A = lo
+        const int col0 = (p % (kTcN / 16)) * 16;
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(w * 32) << 16) + (acc_sel ? kTmemD2Col : 0u) + (uint32_t)col0, r);
         tmem_ld_wait();
-        double* dst = my_part + (size_t)(p * 32) * kTcM;
+        double* dst = my_part + (size_t)(acc_sel * kTcN + col0) * kTcM;
         if (chunk == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(r[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[(size_t)j * kTcM] += (double)__uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] += (double)__uint_as_float(r[j]);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * b);
+      if (lane == 0) mbar_arrive(bar_acc_empty);
     }
   } else if (warp >= 8) {
-    // ===== transform: shift, bf16 hi/lo split, K-major operand store, CUDA-core side sums =====
+    // ===== transform: shift, bf16 hi/lo split, K-major operand store =====
     const int t = warp - 8;
-    const int q = t & 3;        // feature quad: features q*32 .. q*32+31
-    const int gsel = t >> 2;    // row groups {gsel, gsel+2} of each tile
-    const int i = q * 32 + lane;
-    const bool active = i < d;
-    const float c_i = shift_s[active ? i : 0] * (active ? 1.f : 0.f);
-    const float c_y = shift_s[kMaxD];
-    double s1 = 0.0, sxy = 0.0, sy = 0.0, syy = 0.0;
-    long long cnt = 0;
-    const uint32_t st_off = (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
+    const int nq = (d + 31) >> 5;                   // feature quads in use
+    const int n_tasks = nq * kKGroups;              // (quad, 8-row group) tasks per tile
+    const uint32_t esz = sizeof(T);
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      const int rs = it % kRawStages;
-      const uint32_t rph = (it / kRawStages) & 1;
-      const int os = it % kOpStages;
-      const uint32_t oph = (it / kOpStages) & 1;
-      mbar_wait(bar_raw_full + 8 * rs, rph, err, 5);
-      mbar_wait(bar_op_empty + 8 * os, oph ^ 1, err, 6);
+      mbar_wait(bar_raw_full + 8 * rs, rph);
+      mbar_wait(bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
       const int64_t row0 = (tile_begin + it) * kTcRows;
       const bool full_tile = (!has_mask) && (row0 + kTcRows <= n_rows);
-      const T* rawp = reinterpret_cast<const T*>(smem + kOffRaw + rs * kRawStageBytes);
-      const float* yp = reinterpret_cast<const float*>(smem + kOffY + rs * 128);
-      const uint8_t* mp = smem + kOffMask + rs * 128;
-      const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes + st_off;
+      const uint32_t raw_addr = sbase + kOffRaw + rs * kRawStageBytes;
+      const uint32_t m_addr = sbase + kOffMask + rs * 128;
+      const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes;
+      for (int tt = t; tt < n_tasks; tt += kXformWarps) {
+        const int q = tt % nq, g = tt / nq;
+        const int i = q * 32 + lane;
+        const bool active = i < d;
+        const float c_i = shift_s[active ? i : 0];
+        const int r0 = g * 8;
+        float v[8];
+        const uint32_t src = raw_addr + (uint32_t)(r0 * d + (active ? i : 0)) * esz;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int gi = gsel + 2 * half;
-        const int r0 = gi * 8;
-        float v[8], yv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float xv = active ? raw_ld<T>(rawp + (r0 + k) * d + i) : 0.f;
-          v[k] = xv - c_i;
-          yv[k] = yp[r0 + k] - c_y;
-        }
-        int used = 8;
+        for (int k = 0; k < 8; ++k) v[k] = raw_ld_shared<T>(src + (uint32_t)(k * d) * esz) - c_i;
         if (!full_tile) {
-          used = 0;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             bool use = (row0 + r0 + k) < n_rows;
-            if (use && has_mask) use = (mp[r0 + k] == (uint8_t)keep);
-            if (!use) { v[k] = 0.f; yv[k] = 0.f; }
-            used += use ? 1 : 0;
+            if (use && has_mask) use = (ld_shared_u8(m_addr + r0 + k) == (uint32_t)keep);
+            if (!use) v[k] = 0.f;
           }
-        }
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { t1 += v[k]; t2 = fmaf(v[k], yv[k], t2); }
-        s1 += (double)t1;
-        sxy += (double)t2;
-        if (q == 0) {
-          float a = 0.f, bb = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { a += yv[k]; bb = fmaf(yv[k], yv[k], bb); }
-          sy += (double)a;
-          syy += (double)bb;
-          cnt += used;
         }
         uint32_t hp[4], lp[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * p], v[2 * p + 1]);
-          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-          const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * p] - h0, v[2 * p + 1] - h1);
-          hp[p] = hb;
-          lp[p] = *reinterpret_cast<const uint32_t*>(&l);
-        }
+        for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
         if (active) {
-          st_shared_v4(op_addr + gi * kOpLBO, hp);
-          st_shared_v4(op_addr + gi * kOpLBO + (kTcM / 8) * kOpSBO, lp);
+          const uint32_t dst = op_addr + (uint32_t)g * kOpLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
+          st_shared_v4(dst, hp);
+          st_shared_v4(dst + kOpLoOff, lp);
         }
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -418,15 +481,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_arrive(bar_op_full + 8 * os);
         mbar_arrive(bar_raw_empty + 8 * rs);
       }
-    }
-    double* my_side = side + (size_t)blockIdx.x * kTcSideDoubles;
-    my_side[(t * 32 + lane) * 2 + 0] = s1;
-    my_side[(t * 32 + lane) * 2 + 1] = sxy;
-    if (q == 0 && lane == 0) {
-      double* ys = my_side + kTcXformWarps * 32 * 2 + gsel * 3;
-      ys[0] = sy;
-      ys[1] = syy;
-      ys[2] = (double)cnt;
+      if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+      if (++os == kOpStages) { os = 0; oph ^= 1; }
     }
   }
 
@@ -442,10 +498,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------
 // finalize 1: reduce the per-CTA partials in CTA order (deterministic)
-//   red[0 .. 32768)            Gp[col][i]       (col 0..127: hi*hi, col 128..255: hi*lo)
-//   red[32768 + i]             s1[i]  = sum (x_i - c_i)
-//   red[32768 + 128 + i]       sxy[i] = sum (x_i - c_i)(y - c_y)
-//   red[32768 + 256 + 0..2]    sum y', sum y'^2, rows used
+//   red[col * 128 + i], col in [0, 288):  col < 144: D1 (A = hi), col >= 144: D2 (A = lo), columns of [hi | E]
+//   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
 // ------------------------------------------------------------------------------------------
 __global__ void tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
                                  double* __restrict__ red) {
@@ -454,23 +508,10 @@ __global__ void tc_reduce_kernel(const double* __restrict__ part, const double* 
     double s = 0.0;
     for (int c = 0; c < n_ctas; ++c) s += part[(size_t)c * kTcAccElems + idx];
     red[idx] = s;
-  } else if (idx < kTcAccElems + 2 * kMaxD) {
+  } else if (idx < kTcAccElems + 3) {
     const int k = idx - kTcAccElems;
-    const int which = k / kMaxD, i = k % kMaxD;
-    const int q = i >> 5, lane = i & 31;
     double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) {
-      const double* sd = side + (size_t)c * kTcSideDoubles;
-      s += sd[((q)*32 + lane) * 2 + which] + sd[((q + 4) * 32 + lane) * 2 + which];
-    }
-    red[idx] = s;
-  } else if (idx < kTcAccElems + 2 * kMaxD + 3) {
-    const int k = idx - kTcAccElems - 2 * kMaxD;
-    double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) {
-      const double* ys = side + (size_t)c * kTcSideDoubles + kTcXformWarps * 32 * 2;
-      s += ys[k] + ys[3 + k];
-    }
+    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k];
     red[idx] = s;
   }
 }
@@ -484,25 +525,28 @@ __global__ void tc_fold_kernel(const double* __restrict__ red, const float* __re
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dp * dp) return;
   const int a = idx / dp, b = idx % dp;
-  const double* s1 = red + kTcAccElems;
-  const double* sxy = s1 + kMaxD;
-  const double sy = red[kTcAccElems + 2 * kMaxD + 0];
-  const double syy = red[kTcAccElems + 2 * kMaxD + 1];
-  const double n = red[kTcAccElems + 2 * kMaxD + 2];
+  // D1[i][j] = red[j*128 + i], D2[i][j] = red[(144 + j)*128 + i]
+  auto D1 = [&](int i, int j) { return red[(size_t)j * kTcM + i]; };
+  auto D2 = [&](int i, int j) { return red[(size_t)(kTcN + j) * kTcM + i]; };
+  auto s1 = [&](int i) { return D1(i, 128) + D2(i, 128); };                                  // sum (x_i - c_i)
+  auto sxy = [&](int i) { return D1(i, 129) + D1(i, 130) + D2(i, 129) + D2(i, 130); };       // sum (x_i - c_i) y'
+  const double sy = red[kTcAccElems + 0];
+  const double syy = red[kTcAccElems + 1];
+  const double n = red[kTcAccElems + 2];
   const double cy = (double)shift_value(shift, kMaxD, n_rows);
   double val;
   if (a < d && b < d) {
     const double ca = (double)shift_value(shift, a, n_rows), cb = (double)shift_value(shift, b, n_rows);
-    // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hh + hl + hl^T   (lo*lo dropped, ~2^-18 relative)
-    const double hh = 0.5 * (red[(size_t)b * kTcM + a] + red[(size_t)a * kTcM + b]);
-    const double hl = red[(size_t)(kTcM + b) * kTcM + a] + red[(size_t)(kTcM + a) * kTcM + b];
-    val = hh + hl + ca * s1[b] + cb * s1[a] + n * ca * cb;
+    // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hi.hi + lo.hi + hi.lo   (lo.lo dropped, ~2^-18 relative)
+    const double hh = 0.5 * (D1(a, b) + D1(b, a));
+    const double hl = D2(a, b) + D2(b, a);
+    val = hh + hl + ca * s1(b) + cb * s1(a) + n * ca * cb;
   } else if (a < d || b < d) {
     const int i = a < d ? a : b;
     const int o = a < d ? b : a;  // d (ones) or d+1 (y)
     const double ci = (double)shift_value(shift, i, n_rows);
-    if (o == d) val = s1[i] + n * ci;
-    else val = sxy[i] + cy * s1[i] + ci * sy + n * ci * cy;
+    if (o == d) val = s1(i) + n * ci;
+    else val = sxy(i) + cy * s1(i) + ci * sy + n * ci * cy;
   } else if (a == d && b == d) {
     val = n;
   } else if (a == d + 1 && b == d + 1) {
@@ -577,7 +621,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      // rank-1 maps refused: view y as [ceil(n/4)][4] (16-byte rows) -- same bytes land in smem
+      // rank-1 maps refused: view y as [ceil(n/4)][4] (16-byte rows) -- the same bytes land in smem
       cuuint64_t dims2[2] = {4, (cuuint64_t)((n + 3) / 4)};
       cuuint64_t strides2[1] = {16};
       cuuint32_t box2[2] = {4, (cuuint32_t)(kTcRows / 4)};
@@ -592,8 +636,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
       }
     }
   }
-  const bool mask_tma = mask != nullptr && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
-  if (mask != nullptr && !mask_tma) {
+  if (mask != nullptr && (reinterpret_cast<uintptr_t>(mask) & 15) != 0) {
     set_error("row_mask must be 16-byte aligned for the tcgen05 path");
     return B2_E_ARG;
   }
@@ -624,10 +667,11 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   }
 
   if (x_dtype == B2_F32)
-    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n, d, ldx, ctx->shift);
+    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n, d, ldx,
+                                                                  ctx->shift);
   else
-    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y, n, d, ldx,
-                                                                ctx->shift);
+    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y, n,
+                                                                          d, ldx, ctx->shift);
   B2_CUDA(cudaGetLastError());
 
   const int pair = ctx->k_pairs % kKernelEventPairs;
@@ -635,16 +679,16 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   if (x_dtype == B2_F32)
     gram_tc_kernel<float><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
         tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part,
-        ctx->tc_side, nullptr);
+        ctx->tc_side);
   else
     gram_tc_kernel<__nv_bfloat16><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
         tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part,
-        ctx->tc_side, nullptr);
+        ctx->tc_side);
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][1], ctx->stream));
   ctx->k_pairs += 1;
 
-  const int red_elems = kTcAccElems + 2 * kMaxD + 3;
+  const int red_elems = kTcAccElems + 3;
   tc_reduce_kernel<<<(red_elems + 255) / 256, 256, 0, ctx->stream>>>(ctx->tc_part, ctx->tc_side, grid, ctx->tc_red);
   B2_CUDA(cudaGetLastError());
   const int dp = d + 2;

@@ -55,7 +55,7 @@ def test_simt_gram_matches_oracle(ctx, n, d):
     assert S[d, d] == n
 
 
-@pytest.mark.parametrize("n,d", [(32, 128), (4096, 128), (100_003, 128), (50_000, 32), (20_001, 8), (65_536, 64),
+@pytest.mark.parametrize("n,d", [(64, 128), (4096, 128), (100_003, 128), (50_000, 32), (20_001, 8), (65_536, 64),
                                  (9_999, 4), (40_000, 100)])
 def test_tcgen05_gram_matches_oracle(ctx, n, d):
     X, y = orc.generate_dataset(n, d, seed=n + d, dtype=np.float32)
@@ -80,7 +80,7 @@ def test_tcgen05_equals_simt_on_device(ctx):
     assert _rel(a, b) < 2e-6
 
 
-@pytest.mark.parametrize("drain", [32, 1024, 8192, 65536])
+@pytest.mark.parametrize("drain", [64, 1024, 8192, 65536])
 def test_drain_interval_does_not_change_the_fit(ctx, drain):
     X, y = orc.generate_dataset(150_000, 128, seed=5, dtype=np.float32)
     ctx.set_drain_rows(drain)

@@ -44,7 +44,7 @@ def stage_simt():
 def stage_tc():
     from oracle import ols_oracle as orc
     b2, ctx = _ctx()
-    for n, d, drain in ((4096, 128, 8192), (32, 128, 8192), (100_000, 128, 8192), (100_003, 128, 1024),
+    for n, d, drain in ((4096, 128, 8192), (64, 128, 8192), (100_000, 128, 8192), (100_003, 128, 1024),
                         (50_000, 32, 8192), (20_000, 8, 8192), (300_000, 64, 4096)):
         X, y = orc.generate_dataset(n, d, seed=n + d, dtype=np.float32)
         Xd, yd = ctx.to_device(X), ctx.to_device(y)
@@ -54,9 +54,12 @@ def stage_tc():
         ctx.gram_accumulate(Xd, yd)
         S = ctx.gram_export()
         So = orc.gram_stats(X, y)
+        dS = np.abs(S - So)
+        if n <= 2 * d:
+            print(f"tc n={n} d={d}: S rel err {_rel(S, So):.3e} (n <= 2d: no solve)")
+            continue
         fo = orc.fit_from_stats(So)
         coef, b0 = ctx.solve()
-        dS = np.abs(S - So)
         i, j = np.unravel_index(np.argmax(dS), dS.shape)
         print(f"tc n={n} d={d} drain={drain}: S rel err {_rel(S, So):.3e} (worst [{i},{j}] got {S[i, j]:.6e} "
               f"want {So[i, j]:.6e}) | coef linf {np.max(np.abs(coef - fo['coef'])):.3e} "
