@@ -242,12 +242,15 @@ __global__ void tc_shift_kernel(const T* __restrict__ X, const float* __restrict
 // ------------------------------------------------------------------------------------------
 // the Gram kernel
 // ------------------------------------------------------------------------------------------
-template <typename T>
+// DFIX = 128: feature count known at compile time (immediate smem offsets, no index arithmetic in
+// the transform loop); DFIX = 0: runtime d (any multiple of 4 / 8 up to 128).
+template <typename T, int DFIX>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
-               int64_t n_rows, int d, const float* __restrict__ shift, int chunk_tiles,
+               int64_t n_rows, int d_arg, const float* __restrict__ shift, int chunk_tiles,
                double* __restrict__ part, double* __restrict__ side) {
+  const int d = DFIX ? DFIX : d_arg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -367,11 +370,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const uint32_t y_addr = sbase + kOffY + rs * 256;
       const uint32_t m_addr = sbase + kOffMask + rs * 128;
       const uint32_t e_addr = sbase + kOffOp + os * kOpStageBytes + kOpEOff;
+      const int64_t left = n_rows - row0;
+      const int rows_valid = left < kTcRows ? (int)left : kTcRows;
       float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
       for (int h = 0; h < kTcRows / 32; ++h) {
         const int rr = lane + 32 * h;
-        bool use = (row0 + rr) < n_rows;
+        bool use = rr < rows_valid;
         if (use && has_mask) use = (ld_shared_u8(m_addr + rr) == (uint32_t)keep);
         const float yv = use ? ld_shared_f32(y_addr + rr * 4) - c_y : 0.f;
         uint32_t yh, yl;
@@ -433,10 +438,27 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp >= 8) {
     // ===== transform: shift, bf16 hi/lo split, K-major operand store =====
+    // A task = (feature quad q, 8-row group g) of a tile; nq * 8 tasks per tile, at most 2 per warp.
     const int t = warp - 8;
-    const int nq = (d + 31) >> 5;                   // feature quads in use
-    const int n_tasks = nq * kKGroups;              // (quad, 8-row group) tasks per tile
+    const int nq = (d + 31) >> 5;
     const uint32_t esz = sizeof(T);
+    const uint32_t pitch = (uint32_t)d * esz;       // raw tile row pitch in bytes
+    bool tv[2];
+    float tc[2];
+    uint32_t tsrc[2], tdst[2];
+    int tr0[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int tt = t + kXformWarps * s;
+      const bool valid = tt < nq * kKGroups;
+      const int q = valid ? tt % nq : 0, g = valid ? tt / nq : 0;
+      const int i = q * 32 + lane;
+      tv[s] = valid && (i < d);
+      tc[s] = shift_s[tv[s] ? i : 0];
+      tr0[s] = g * 8;
+      tsrc[s] = (uint32_t)(g * 8) * pitch + (uint32_t)(tv[s] ? i : 0) * esz;
+      tdst[s] = (uint32_t)g * kOpLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
+    }
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -444,35 +466,33 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
       const int64_t row0 = (tile_begin + it) * kTcRows;
-      const bool full_tile = (!has_mask) && (row0 + kTcRows <= n_rows);
+      const int64_t left = n_rows - row0;
+      const int rows_valid = left < kTcRows ? (int)left : kTcRows;
+      const bool full_tile = (!has_mask) && (rows_valid == kTcRows);
       const uint32_t raw_addr = sbase + kOffRaw + rs * kRawStageBytes;
       const uint32_t m_addr = sbase + kOffMask + rs * 128;
       const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes;
-      for (int tt = t; tt < n_tasks; tt += kXformWarps) {
-        const int q = tt % nq, g = tt / nq;
-        const int i = q * 32 + lane;
-        const bool active = i < d;
-        const float c_i = shift_s[active ? i : 0];
-        const int r0 = g * 8;
-        float v[8];
-        const uint32_t src = raw_addr + (uint32_t)(r0 * d + (active ? i : 0)) * esz;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = raw_ld_shared<T>(src + (uint32_t)(k * d) * esz) - c_i;
-        if (!full_tile) {
+      for (int s = 0; s < 2; ++s) {
+        if (tv[s]) {
+          float v[8];
+          const uint32_t src = raw_addr + tsrc[s];
+          const float c_i = tc[s];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            bool use = (row0 + r0 + k) < n_rows;
-            if (use && has_mask) use = (ld_shared_u8(m_addr + r0 + k) == (uint32_t)keep);
-            if (!use) v[k] = 0.f;
+          for (int k = 0; k < 8; ++k) v[k] = raw_ld_shared<T>(src + (uint32_t)k * pitch) - c_i;
+          if (!full_tile) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              bool use = (tr0[s] + k) < rows_valid;
+              if (use && has_mask) use = (ld_shared_u8(m_addr + tr0[s] + k) == (uint32_t)keep);
+              if (!use) v[k] = 0.f;
+            }
           }
-        }
-        uint32_t hp[4], lp[4];
+          uint32_t hp[4], lp[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
-        if (active) {
-          const uint32_t dst = op_addr + (uint32_t)g * kOpLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
-          st_shared_v4(dst, hp);
-          st_shared_v4(dst + kOpLoOff, lp);
+          for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
+          st_shared_v4(op_addr + tdst[s], hp);
+          st_shared_v4(op_addr + tdst[s] + kOpLoOff, lp);
         }
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -660,8 +680,11 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   if (chunk_tiles < 1) chunk_tiles = 1;
 
   if (!ctx->tc_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSmemBytes));
+    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kSmemBytes));
     ctx->tc_attr_set = true;
   }
@@ -676,14 +699,16 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
-  if (x_dtype == B2_F32)
-    gram_tc_kernel<float><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
-        tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part,
-        ctx->tc_side);
-  else
-    gram_tc_kernel<__nv_bfloat16><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
-        tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part,
-        ctx->tc_side);
+#define B2_LAUNCH_TC(T, DF)                                                                              \
+  gram_tc_kernel<T, DF><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                    \
+      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part, \
+      ctx->tc_side)
+  if (x_dtype == B2_F32) {
+    if (d == 128) B2_LAUNCH_TC(float, 128); else B2_LAUNCH_TC(float, 0);
+  } else {
+    if (d == 128) B2_LAUNCH_TC(__nv_bfloat16, 128); else B2_LAUNCH_TC(__nv_bfloat16, 0);
+  }
+#undef B2_LAUNCH_TC
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][1], ctx->stream));
   ctx->k_pairs += 1;

@@ -5,7 +5,7 @@ Tolerances (stated once):
   * CUDA-core Gram (fp64 accumulation of exact products): S within 1e-12 relative of the fp64 oracle.
   * tcgen05 Gram (bf16 hi/lo operands, fp32 TMEM accumulation drained every 8192 rows, fp64 beyond):
     coefficient l_inf error < 1e-4 against the fit of the same rows (BASELINE.json north_star); measured
-    values are ~1e-6, asserted at 2e-5 to catch regressions.  intercept_ within 5e-3 (ill-conditioned:
+    values are ~1e-6, asserted at 2e-5 to catch regressions.  intercept_ within 3e-2 (ill-conditioned:
     leverage x_bar * sqrt(D)).
   * metrics: relative 1e-5 (y is staged as fp32).
 """
@@ -22,7 +22,7 @@ from oracle import ols_oracle as orc
 pytestmark = pytest.mark.gpu
 
 COEF_TOL = 2e-5      # asserted; the contract is 1e-4
-INTERCEPT_TOL = 5e-3
+INTERCEPT_TOL = 3e-2   # |d b0| <= sum_j |xbar_j| |d beta_j| ~ D * 50 * coef error
 
 
 def _rel(a, b):
