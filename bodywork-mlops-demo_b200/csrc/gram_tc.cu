@@ -11,11 +11,12 @@
 //     --> smem operand tile, K-major canonical layout (8 x 16 B core matrices, no swizzle):
 //            rows j = 0..127 hi | 128..143 E | 144..271 lo        (one 16-byte chunk = 8 consecutive rows of X)
 //     --tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128, N=144, K=16, two per K-step:
-//            D1[i][j] += sum_r hi[r][i] * [hi | E][r][j]      TMEM columns   0..143
-//            D2[i][j] += sum_r lo[r][i] * [hi | E][r][j]      TMEM columns 256..399
+//            D1[i][j] += sum_r hi[r][i] * [hi | E][r][j]      TMEM columns 0..143 / 160..303 (double buffered)
+//            D2[i][j] += sum_r lo[r][i] * [hi | E][r][j]      TMEM columns 320..463 (never drained mid-kernel)
 //        so D1[:, :128] = hi^T hi, D2[:, :128] = lo^T hi, column 128 = sum v, columns 129/130 = sum v*y'.
-//     --every `drain_rows` rows: epilogue warps tcgen05.ld both accumulators and fold them into this
-//        CTA's fp64 partial in global memory (L2 resident).
+//     --every `drain_rows` rows: epilogue warps tcgen05.ld the D1 buffer just finished and fold it into this
+//        CTA's fp64 partial in global memory while the MMAs continue into the other D1 buffer; D2 holds
+//        only the small zero-mean lo terms, so its fp32 sums are drained once at the end.
 //
 // Why the shift and the split: the tensor core accumulates fp32 with truncation, so raw (uncentred)
 // second moments cannot reach the 1e-4 coefficient tolerance; after the shift the Gram is ~diagonal and
@@ -25,6 +26,7 @@
 // The finalize kernels reduce the per-CTA partials in a fixed order (deterministic), undo the shift in
 // fp64 and add the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "b2_internal.cuh"
 
@@ -52,12 +54,13 @@ constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;     // 131072
 constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;         // 200704
 constexpr uint32_t kOffMask = kOffY + kRawStages * 256;
 constexpr uint32_t kOffBar = kOffMask + kRawStages * 128;
-constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 2;
+constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 4;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
 constexpr uint32_t kSmemBytes = kOffShift + (kMaxD + 4) * 4 + 1024;    // + alignment slack (~204 KB)
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-constexpr uint32_t kTmemD2Col = 256;                                   // second accumulator's first column
+constexpr uint32_t kTmemD1Stride = 160;   // D1 (A = hi) is double buffered: columns 0..143 and 160..303
+constexpr uint32_t kTmemD2Col = 320;      // D2 (A = lo): columns 320..463, accumulates for the whole kernel
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=144, M=128 (cute::UMMA::InstrDescriptor layout)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
@@ -86,7 +89,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // Wait with a hardware suspend hint (the thread sleeps inside try_wait and is woken by the arrive, so
 // waiting warps do not burn issue slots).  Bounded: a protocol bug must end in a trap (a clean launch
 // failure), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
   uint32_t done = 0;
   uint64_t t0 = 0;
   while (true) {
@@ -95,7 +98,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
         : "memory");
     if (done) break;
     const uint64_t now = globaltimer_ns();
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
                int64_t n_rows, int d_arg, const float* __restrict__ shift, int chunk_tiles,
-               double* __restrict__ part, double* __restrict__ side) {
+               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg) {
   const int d = DFIX ? DFIX : d_arg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -261,8 +264,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t bar_raw_empty = bar_raw_full + 8 * kRawStages;        // [kRawStages]
   const uint32_t bar_op_full = bar_raw_empty + 8 * kRawStages;         // [kOpStages]
   const uint32_t bar_op_empty = bar_op_full + 8 * kOpStages;           // [kOpStages]
-  const uint32_t bar_acc_full = bar_op_empty + 8 * kOpStages;          // [1]
-  const uint32_t bar_acc_empty = bar_acc_full + 8;                     // [1]
+  const uint32_t bar_acc_full = bar_op_empty + 8 * kOpStages;          // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;                    // [2]
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* shift_s = reinterpret_cast<float*>(smem + kOffShift);
 
@@ -283,8 +286,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(bar_op_full + 8 * s, kProducers);
       mbar_init(bar_op_empty + 8 * s, 1);
     }
-    mbar_init(bar_acc_full, 1);
-    mbar_init(bar_acc_empty, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -292,7 +297,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmY);
     if (has_mask) tma_prefetch_desc(&tmM);
   }
-  if (warp == 1) {  // TMEM: 512 columns (accumulators at 0..143 and 256..399)
+  if (warp == 1) {  // TMEM: 512 columns (D1 x2 at 0 / 160, D2 at 320)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + kOffTmemPtr)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -316,7 +321,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(bar_raw_empty + 8 * s, ph ^ 1);
+        mbar_wait(bar_raw_empty + 8 * s, ph ^ 1, wait_ns);
         const uint32_t full = bar_raw_full + 8 * s;
         mbar_expect_tx(full, tx);
         const int64_t row0 = (tile_begin + it) * kTcRows;
@@ -334,24 +339,25 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        if (in_chunk == 0) {  // the single TMEM accumulator pair must have been drained
-          mbar_wait(bar_acc_empty, (chunk & 1) ^ 1);
+        const int b = chunk & 1;
+        if (in_chunk == 0) {  // this D1 buffer must have been drained (two chunks ago)
+          mbar_wait(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        mbar_wait(bar_op_full + 8 * os, oph);
+        mbar_wait(bar_op_full + 8 * os, oph, wait_ns);
         tc_fence_after();
         const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes;
+        const uint32_t tmem_d1 = tmem_base + (uint32_t)b * kTmemD1Stride;
 #pragma unroll
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
           const uint64_t b_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO);               // [hi | E], also A = hi
           const uint64_t lo_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO + kOpLoOff);   // A = lo
-          const uint32_t acc = (in_chunk > 0 || k2 > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, b_desc, b_desc, acc);
-          umma_bf16(tmem_base + kTmemD2Col, lo_desc, b_desc, acc);
+          if (!(dbg & 2u)) umma_bf16(tmem_d1, b_desc, b_desc, (in_chunk > 0 || k2 > 0) ? 1u : 0u);
+          if (!(dbg & 3u)) umma_bf16(tmem_base + kTmemD2Col, lo_desc, b_desc, (it > 0 || k2 > 0) ? 1u : 0u);
         }
         umma_commit(bar_op_empty + 8 * os);  // frees the operand stage when these MMAs retire
         const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
-        if (last) { umma_commit(bar_acc_full); in_chunk = 0; ++chunk; }
+        if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
         else ++in_chunk;
         if (++os == kOpStages) { os = 0; oph ^= 1; }
       }
@@ -363,8 +369,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      mbar_wait(bar_raw_full + 8 * rs, rph);
-      mbar_wait(bar_op_empty + 8 * os, oph ^ 1);
+      mbar_wait(bar_raw_full + 8 * rs, rph, wait_ns);
+      mbar_wait(bar_op_empty + 8 * os, oph ^ 1, wait_ns);
       tc_fence_after();
       const int64_t row0 = (tile_begin + it) * kTcRows;
       const uint32_t y_addr = sbase + kOffY + rs * 256;
@@ -413,17 +419,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // ===== epilogue: TMEM -> registers -> fp64 partial in global (column-major [col][feature]) =====
     const int w = warp & 3;  // TMEM lane quadrant this warp may access
     double* my_part = part + (size_t)blockIdx.x * kTcAccElems + w * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      mbar_wait(bar_acc_full, chunk & 1);
+      const int b = chunk & 1;
+      mbar_wait(bar_acc_full + 8 * b, (chunk >> 1) & 1);
       tc_fence_after();
+      // D1 (A = hi) of this chunk: fold into partial columns [0, 144)
 #pragma unroll 1
-      for (int p = 0; p < kTcAccCols / 16; ++p) {
-        const int acc_sel = p / (kTcN / 16);          // 0: A = hi, 1: A = lo
-        const int col0 = (p % (kTcN / 16)) * 16;
+      for (int p = 0; p < kTcN / 16; ++p) {
         uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(w * 32) << 16) + (acc_sel ? kTmemD2Col : 0u) + (uint32_t)col0, r);
+        tmem_ld16(lane_base + (uint32_t)b * kTmemD1Stride + (uint32_t)(p * 16), r);
         tmem_ld_wait();
-        double* dst = my_part + (size_t)(acc_sel * kTcN + col0) * kTcM;
+        double* dst = my_part + (size_t)(p * 16) * kTcM;
         if (chunk == 0) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(r[j]);
@@ -434,7 +441,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty);
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * b);
+    }
+    // D2 (A = lo) accumulated over the whole range (small zero-mean sums): partial columns [144, 288)
+    tc_fence_after();
+#pragma unroll 1
+    for (int p = 0; p < kTcN / 16; ++p) {
+      uint32_t r[16];
+      tmem_ld16(lane_base + kTmemD2Col + (uint32_t)(p * 16), r);
+      tmem_ld_wait();
+      double* dst = my_part + (size_t)(kTcN + p * 16) * kTcM;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(r[j]);
     }
   } else if (warp >= 8) {
     // ===== transform: shift, bf16 hi/lo split, K-major operand store =====
@@ -462,8 +480,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      mbar_wait(bar_raw_full + 8 * rs, rph);
-      mbar_wait(bar_op_empty + 8 * os, oph ^ 1);
+      mbar_wait(bar_raw_full + 8 * rs, rph, wait_ns);
+      mbar_wait(bar_op_empty + 8 * os, oph ^ 1, wait_ns);
       tc_fence_after();
       const int64_t row0 = (tile_begin + it) * kTcRows;
       const int64_t left = n_rows - row0;
@@ -479,7 +497,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const uint32_t src = raw_addr + tsrc[s];
           const float c_i = tc[s];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = raw_ld_shared<T>(src + (uint32_t)k * pitch) - c_i;
+          for (int k = 0; k < 8; ++k)
+            v[k] = ((dbg & 8u) ? __uint_as_float(src + k) : raw_ld_shared<T>(src + (uint32_t)k * pitch)) - c_i;
           if (!full_tile) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -491,11 +510,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           uint32_t hp[4], lp[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
-          st_shared_v4(op_addr + tdst[s], hp);
-          st_shared_v4(op_addr + tdst[s] + kOpLoOff, lp);
+          if (!(dbg & 4u)) {
+            st_shared_v4(op_addr + tdst[s], hp);
+            st_shared_v4(op_addr + tdst[s] + kOpLoOff, lp);
+          }
         }
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      if (!(dbg & 32u)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_op_full + 8 * os);
@@ -697,12 +718,20 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
                                                                           d, ldx, ctx->shift);
   B2_CUDA(cudaGetLastError());
 
+  static const uint32_t wait_ns = []() {   // development knob: suspend-time hint of the pipeline waits
+    const char* e = getenv("B2_WAIT_HINT_NS");
+    return e ? (uint32_t)atoi(e) : 20000u;
+  }();
+  static const uint32_t dbg = []() {       // development knob: bit0 skip MMA2, bit1 skip all MMAs, bit2 skip STS, bit3 skip LDS
+    const char* e = getenv("B2_TC_DEBUG");
+    return e ? (uint32_t)atoi(e) : 0u;
+  }();
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
 #define B2_LAUNCH_TC(T, DF)                                                                              \
   gram_tc_kernel<T, DF><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                    \
       tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part, \
-      ctx->tc_side)
+      ctx->tc_side, wait_ns, dbg)
   if (x_dtype == B2_F32) {
     if (d == 128) B2_LAUNCH_TC(float, 128); else B2_LAUNCH_TC(float, 0);
   } else {
