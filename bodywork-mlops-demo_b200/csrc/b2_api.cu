@@ -3,6 +3,7 @@
 // (pinned ring -> HBM staging, copy/compute overlap), NCCL all-reduce of the statistic, timing.
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -385,7 +386,11 @@ int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double*
   if (!(alpha >= 0.0)) { set_error("alpha must be >= 0"); return B2_E_ARG; }
   if (int r = launch_solve_cholesky(ctx, alpha, fit_intercept)) return r;
   double info = 0.0;
-  if (int r = fetch_solution(ctx, coef, intercept, nullptr, nullptr, &info)) return r;
+  double phase[kMaxD];
+  if (int r = fetch_solution(ctx, coef, intercept, getenv("B2_SOLVE_TIMING") ? phase : nullptr, nullptr, &info)) return r;
+  if (getenv("B2_SOLVE_TIMING"))
+    fprintf(stderr, "[b2_solve] cycles: build %.0f diag %.0f panel %.0f update %.0f backward %.0f\n", phase[0], phase[1],
+            phase[2], phase[3], phase[4]);
   if (info != 0.0) {
     set_error("Cholesky pivot %d is not positive: the centred Gram matrix is rank deficient "
               "(use alpha > 0 or b2_solve_spectral)", (int)info);

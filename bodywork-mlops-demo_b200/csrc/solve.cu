@@ -32,83 +32,240 @@ __device__ void build_normal_equations(const double* __restrict__ S, int d, doub
   for (int j = threadIdx.x; j < d; j += blockDim.x) mean[j] = fit_intercept ? S[j * dp + d] * inv_n : 0.0;
   __syncthreads();
   const double ybar = fit_intercept ? S[d * dp + d + 1] * inv_n : 0.0;
-  for (int idx = threadIdx.x; idx < d * d; idx += blockDim.x) {
-    const int i = idx / d, j = idx - i * d;
-    // symmetrise explicitly; centre with n * mean_i * mean_j
-    double v = 0.5 * (S[i * dp + j] + S[j * dp + i]) - n * mean[i] * mean[j];
-    if (i == j) v += alpha;
-    A[i * pitch + j] = v;
+  // one warp per row, coalesced; S is symmetric by construction (tc_fold / the SIMT reduce write both halves)
+  for (int i = threadIdx.x >> 5; i < d; i += blockDim.x >> 5) {
+    const double mi = mean[i];
+    for (int j = threadIdx.x & 31; j < d; j += 32) {
+      double v = S[i * dp + j] - n * mi * mean[j];
+      if (i == j) v += alpha;
+      A[i * pitch + j] = v;
+    }
   }
   for (int i = threadIdx.x; i < d; i += blockDim.x) r[i] = S[i * dp + d + 1] - n * mean[i] * ybar;
   if (threadIdx.x == 0) *ybar_out = ybar;
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSolveThreads, 1)
+// 1/sqrt(x) for normal positive x without the library's slow-path call (a call inside the unrolled pivot
+// loop forces the register-resident block onto the stack): scale x by an even power of two into [1, 4),
+// fp32 MUFU seed, two Newton steps in fp64 (2^-23 -> 2^-45 -> below 2^-53), undo the scaling.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int e2 = ((((hi >> 20) & 0x7ff) - 1023)) & ~1;                 // even exponent
+  const double xs = __hiloint2double(hi - (e2 << 20), lo);              // x * 2^-e2 in [1, 4)
+  double y = (double)rsqrtf((float)xs);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double t = xs * y, h = 0.5 * y;
+    const double e = fma(-t, h, 0.5);
+    y = fma(y, e, y);
+  }
+  return __hiloint2double(__double2hiint(y) - ((e2 >> 1) << 20), __double2loint(y));   // y * 2^-(e2/2)
+}
+
+// Blocked right-looking Cholesky (block 16) of the augmented matrix [A ; r^T]: carrying r as one extra
+// row through the panel/update steps leaves z = L^-1 r in that row, so no forward substitution is needed.
+// fp64 arithmetic on this part has ~25-cycle dependent latency, so every phase is written to keep the
+// dependent chains short:
+//   (1) diagonal block: one warp, rows in registers, pivots/multipliers by shuffle, no selects (the part of
+//       a row right of the diagonal may hold garbage -- it is never read), rsqrt_pos instead of sqrt/div;
+//   (2) panel: one thread per row, "right-looking" inside the row (2 dependent ops per column);
+//   (3) trailing update: 4 independent accumulators per thread;
+//   (4) back substitution per block in registers + shuffles.
+// A is (d+1) x (d+1) with row pitch d+1 (fp64, shared memory); row d = r^T.
+constexpr int kNB = 16;
+constexpr int kCholThreads = 512;
+
+__global__ void __launch_bounds__(kCholThreads, 1)
 solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit_intercept,
                       double* __restrict__ out) {
   extern __shared__ double sm[];
   const int pitch = d + 1;
-  double* A = sm;                  // d x (d+1)
-  double* r = A + d * pitch;       // d
-  double* mean = r + d;            // d
-  double* misc = mean + d;         // [0] ybar, [1] max diag, [2] info
+  double* A = sm;                        // rows 0..d-1 = A, row d = r^T
+  double* r = A + d * pitch;             // alias of row d
+  double* mean = A + (d + 1) * pitch;    // d
+  double* invd = mean + d;               // d: 1 / L[k][k]
+  double* misc = invd + d;               // [0] ybar, [1] max diag, [2] info (1-based failing pivot, 0 = ok)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  long long tm[5] = {0, 0, 0, 0, 0};     // phase cycle counters: build, diag, panel, update, backward
+  long long tc0 = clock64();
   build_normal_equations(S, d, alpha, fit_intercept, A, r, mean, &misc[0]);
-  if (threadIdx.x == 0) {
+  tm[0] = clock64() - tc0;
+  if (warp == 0) {
     double mx = 0.0;
-    for (int i = 0; i < d; ++i) mx = fmax(mx, A[i * pitch + i]);
-    misc[1] = mx;
-    misc[2] = 0.0;
+    for (int i = lane; i < d; i += 32) mx = fmax(mx, A[i * pitch + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) { misc[1] = mx; misc[2] = 0.0; }
   }
   __syncthreads();
   const double tiny = misc[1] * 1e-12;
+  const int rows = d + 1;                // including the augmented row
 
-  // right-looking Cholesky, lower triangle in place
-  for (int k = 0; k < d; ++k) {
-    if (threadIdx.x == 0) {
-      const double piv = A[k * pitch + k];
-      if (!(piv > tiny)) { misc[2] = (double)(k + 1); A[k * pitch + k] = 1.0; }
-      else A[k * pitch + k] = sqrt(piv);
+  for (int kb = 0; kb < d; kb += kNB) {
+    const int nb = (d - kb) < kNB ? (d - kb) : kNB;
+    tc0 = clock64();
+    // ---- (1) diagonal block -------------------------------------------------------------------------
+    if (warp == 0) {
+      if (nb == kNB) {
+        double a[kNB];
+        const int row = kb + (lane & (kNB - 1));
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) a[c] = A[row * pitch + kb + c];   // full row; only c <= lane is meaningful
+        double my_inv = 1.0;
+        int first_bad = 0;
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) {
+          const double piv = __shfl_sync(0xffffffffu, a[k], k);
+          const bool bad = !(piv > tiny);
+          const double inv = bad ? 1.0 : rsqrt_pos(piv);
+          const double l = a[k] * inv;                  // lane > k: L[r][k]; lane == k: sqrt(piv)
+          a[k] = l;
+          my_inv = (lane == k) ? inv : my_inv;
+          first_bad = (bad && first_bad == 0) ? (kb + k + 1) : first_bad;
+#pragma unroll
+          for (int c = k + 1; c < kNB; ++c) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);
+        }
+        if (lane < kNB) {
+#pragma unroll
+          for (int c = 0; c < kNB; ++c) if (c <= lane) A[row * pitch + kb + c] = a[c];
+          invd[kb + lane] = my_inv;
+        }
+        if (lane == 0 && first_bad != 0 && misc[2] == 0.0) misc[2] = (double)first_bad;
+      } else {   // ragged last block (d % 16 != 0): plain shared-memory version
+        const int row = kb + lane;
+        for (int k = 0; k < nb; ++k) {
+          const int kk = kb + k;
+          const double piv = A[kk * pitch + kk];
+          __syncwarp();
+          const bool bad = !(piv > tiny);
+          const double inv = bad ? 1.0 : rsqrt_pos(piv);
+          if (lane == k) {
+            if (bad && misc[2] == 0.0) misc[2] = (double)(kk + 1);
+            A[kk * pitch + kk] = bad ? 1.0 : piv * inv;
+            invd[kk] = inv;
+          }
+          double l = 0.0;
+          if (lane > k && lane < nb) {
+            l = A[row * pitch + kk] * inv;
+            A[row * pitch + kk] = l;
+          }
+          __syncwarp();
+          if (lane > k && lane < nb)
+            for (int c = k + 1; c <= lane; ++c) A[row * pitch + kb + c] -= l * A[(kb + c) * pitch + kk];
+          __syncwarp();
+        }
+      }
     }
     __syncthreads();
+    tm[1] += clock64() - tc0; tc0 = clock64();
     if (misc[2] != 0.0) break;
-    const double inv = 1.0 / A[k * pitch + k];
-    for (int i = k + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * pitch + k] *= inv;
-    __syncthreads();
-    // trailing update: element (i, j), k < j <= i ; 2 threads per row
-    const int rows = d - k - 1;
-    for (int t = threadIdx.x; t < rows * 2; t += blockDim.x) {
-      const int i = k + 1 + (t >> 1);
-      const double lik = A[i * pitch + k];
-      for (int j = k + 1 + (t & 1); j <= i; j += 2) A[i * pitch + j] -= lik * A[j * pitch + k];
+    // ---- (2) panel: rows below the block (incl. the r row): x L_bb^T = a ----------------------------------
+    const int below = rows - kb - nb;
+    for (int t = tid; t < below; t += blockDim.x) {
+      const int i = kb + nb + t;
+      double sv[kNB];
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) sv[c] = c < nb ? A[i * pitch + kb + c] : 0.0;
+#pragma unroll
+      for (int m = 0; m < kNB; ++m) {
+        if (m < nb) {
+          const double xm = sv[m] * invd[kb + m];
+          sv[m] = xm;
+#pragma unroll
+          for (int c = m + 1; c < kNB; ++c) if (c < nb) sv[c] = fma(-xm, A[(kb + c) * pitch + kb + m], sv[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kNB; ++c) if (c < nb) A[i * pitch + kb + c] = sv[c];
     }
     __syncthreads();
+    tm[2] += clock64() - tc0; tc0 = clock64();
+    // ---- (3) trailing update A[i][j] -= sum_m P[i][m] P[j][m], i >= j >= kb+nb (i up to the r row) -----------
+    const int ty = tid >> 4, tx = tid & 15;           // 32 x 16 thread tile
+    const int base = kb + nb;
+    for (int i = base + ty; i < rows; i += kCholThreads / 16) {
+      double pi[kNB];
+#pragma unroll
+      for (int m = 0; m < kNB; ++m) pi[m] = m < nb ? A[i * pitch + kb + m] : 0.0;
+      const int jmax = i < d ? i : d - 1;
+      for (int j0 = base + tx; j0 <= jmax; j0 += 64) {   // 4 columns (stride 16) per pass: independent chains
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int m = 0; m < kNB; ++m) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 16 * u;
+            const double pj = (m < nb && j <= jmax) ? A[j * pitch + kb + m] : 0.0;
+            acc[u] = fma(pi[m], pj, acc[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 16 * u;
+          if (j <= jmax) A[i * pitch + j] -= acc[u];
+        }
+      }
+    }
+    __syncthreads();
+    tm[3] += clock64() - tc0;
   }
+  tc0 = clock64();
   const bool singular = misc[2] != 0.0;
   if (!singular) {
-    // forward: L z = r (column oriented)
-    for (int k = 0; k < d; ++k) {
-      if (threadIdx.x == 0) r[k] /= A[k * pitch + k];
+    // row d now holds z = L^-1 r.  backward: L^T b = z, blocked from the bottom
+    for (int kb = ((d - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+      const int nb = (d - kb) < kNB ? (d - kb) : kNB;
+      if (warp == 0) {
+        if (nb == kNB) {
+          const int col = lane & (kNB - 1);
+          double lt[kNB];                                // lt[k] = L[kb+k][kb+col]
+#pragma unroll
+          for (int k = 0; k < kNB; ++k) lt[k] = A[(kb + k) * pitch + kb + col];
+          double z = r[kb + col];
+          const double dinv = invd[kb + col];
+#pragma unroll
+          for (int k = kNB - 1; k >= 0; --k) {
+            const double bk = __shfl_sync(0xffffffffu, z * dinv, k);
+            z = (lane == k) ? bk : ((lane < k) ? fma(-lt[k], bk, z) : z);   // lanes > k are already final
+          }
+          if (lane < kNB) r[kb + lane] = z;
+        } else {
+          for (int k = nb - 1; k >= 0; --k) {
+            if (lane == k) r[kb + k] *= invd[kb + k];
+            __syncwarp();
+            if (lane < k) r[kb + lane] -= A[(kb + k) * pitch + kb + lane] * r[kb + k];
+            __syncwarp();
+          }
+        }
+      }
       __syncthreads();
-      const double zk = r[k];
-      for (int i = k + 1 + threadIdx.x; i < d; i += blockDim.x) r[i] -= A[i * pitch + k] * zk;
-      __syncthreads();
-    }
-    // backward: L^T b = z
-    for (int k = d - 1; k >= 0; --k) {
-      if (threadIdx.x == 0) r[k] /= A[k * pitch + k];
-      __syncthreads();
-      const double bk = r[k];
-      for (int i = threadIdx.x; i < k; i += blockDim.x) r[i] -= A[k * pitch + i] * bk;
+      for (int i = tid; i < kb; i += blockDim.x) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < kNB; m += 2) {
+          if (m < nb) acc0 = fma(A[(kb + m) * pitch + i], r[kb + m], acc0);
+          if (m + 1 < nb) acc1 = fma(A[(kb + m + 1) * pitch + i], r[kb + m + 1], acc1);
+        }
+        r[i] -= acc0 + acc1;
+      }
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) out[i] = singular ? 0.0 : r[i];
-  if (threadIdx.x == 0) {
-    double b0 = misc[0];
-    if (!singular) for (int i = 0; i < d; ++i) b0 -= mean[i] * r[i];
-    out[kOutIntercept] = singular ? 0.0 : b0;
-    out[kOutInfo] = misc[2];
+  tm[4] = clock64() - tc0;
+  if (tid == 0)
+    for (int k = 0; k < 5; ++k) out[kOutSingular + k] = (double)tm[k];
+  for (int i = tid; i < d; i += blockDim.x) out[i] = singular ? 0.0 : r[i];
+  if (warp == 0) {
+    double part = 0.0;
+    for (int i = lane; i < d; i += 32) part += mean[i] * r[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) {
+      out[kOutIntercept] = singular ? 0.0 : misc[0] - part;
+      out[kOutInfo] = misc[2];
+    }
   }
 }
 
@@ -230,14 +387,14 @@ solve_spectral_kernel(const double* __restrict__ S, int d, double cond, int fit_
   }
 }
 
-size_t solve_smem_bytes(int d) { return sizeof(double) * ((size_t)d * (d + 1) + 3 * d + 8); }
+size_t solve_smem_bytes(int d) { return sizeof(double) * ((size_t)(d + 1) * (d + 1) + 3 * d + 8); }
 
 }  // namespace
 
 int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept) {
   const size_t smem = solve_smem_bytes(ctx->d);
   B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  solve_cholesky_kernel<<<1, kSolveThreads, smem, ctx->stream>>>(ctx->S, ctx->d, alpha, fit_intercept,
+  solve_cholesky_kernel<<<1, kCholThreads, smem, ctx->stream>>>(ctx->S, ctx->d, alpha, fit_intercept,
                                                                  ctx->solve_out);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 1;
