@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -55,44 +54,75 @@ def ncu_traffic_per_launch(workload_key: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region, polled in-process through NVML every ~2 ms
+    (the timed region of a 20-step run is ~20 ms -- too short for an `nvidia-smi -lms` subprocess to start).
+    Falls back to the B200_PROFILING.md nvidia-smi recipe when pynvml is unavailable."""
+    _REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, device: int):
-        self.device, self.proc, self.tmp = device, None, None
+        self.device, self.samples, self.stop_flag, self.thread, self.h = device, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # torchrun may remap devices through CUDA_VISIBLE_DEVICES; NVML indexes physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device]) if vis and vis.split(",")[device].isdigit() else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.device), "-lms", "50"], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nv is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= int(s[1])
+        reasons = [name for name, bit in self._REASONS if mask & bit]
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.tmp.flush()
-        rows = [ln.split(",") for ln in open(self.tmp.name).read().strip().splitlines() if ln.count(",") >= 8]
-        os.unlink(self.tmp.name)
-        if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = set()
-        for r in rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+            mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(mx) if mx else None, "samples": len(sm),
+                "power_w_max": max(s[2] for s in self.samples), "reasons": reasons, "how": "NVML poll, 2 ms"}
+
+    def _smi_once(self) -> dict:
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                  str(self.device)], capture_output=True, text=True, timeout=10).stdout.strip()
+            f = [x.strip() for x in out.split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "samples": 1, "power_w_max": float(f[2]),
+                    "reasons": [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")],
+                    "how": "nvidia-smi, one sample right after the timed region"}
+        except Exception as exc:  # pragma: no cover
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"unavailable: {exc}"]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -127,6 +157,11 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     import sklearn  # noqa: F401  (the reference's dependency; pinned 0.24.0 upstream, 1.9.0 in this image)
+    try:   # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host thread BLAS will take
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     t_cal = sklearn_fit_rows_per_s(32_768)[1]
     budget = 150.0 / max(args.steps + args.warmup, 1)
     rows = int(min(1_000_000, max(32_768, 32_768 * budget / max(t_cal, 1e-3) * 0.5)))
@@ -315,7 +350,7 @@ def main() -> None:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 hi+lo tensor-core operands, fp32 TMEM accumulate, fp64 fold/solve",
+            "vs_baseline": None, "dtype": "bf16x2 (hi+lo) MMA operands, f32 accumulate, f64 fold+solve",
             "data": "synthetic (device Philox, reference DGP: X~U(0,100), y=1+0.5*sum(X)+10*eps)",
             "config": workload_config(world, kind), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
