@@ -68,7 +68,7 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("B2_LIB_PATH") or _build.LIB_PATH   # B2_LIB_PATH: development override (kernel variants)
 
 
 def load():
@@ -77,7 +77,9 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path) or (_build.is_stale() and os.environ.get("B2_NO_REBUILD") != "1"):
+    if os.environ.get("B2_LIB_PATH"):
+        pass
+    elif not os.path.exists(path) or (_build.is_stale() and os.environ.get("B2_NO_REBUILD") != "1"):
         try:
             _build.build()
         except Exception as exc:  # pragma: no cover - only without nvcc

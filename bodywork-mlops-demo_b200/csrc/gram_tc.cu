@@ -59,8 +59,14 @@ constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
 constexpr uint32_t kSmemBytes = kOffShift + (kMaxD + 4) * 4 + 1024;    // + alignment slack (~204 KB)
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-constexpr uint32_t kTmemD1Stride = 160;   // D1 (A = hi) is double buffered: columns 0..143 and 160..303
-constexpr uint32_t kTmemD2Col = 320;      // D2 (A = lo): columns 320..463, accumulates for the whole kernel
+#ifndef B2_TMEM_D1_STRIDE
+#define B2_TMEM_D1_STRIDE 160
+#endif
+#ifndef B2_TMEM_D2_COL
+#define B2_TMEM_D2_COL 320
+#endif
+constexpr uint32_t kTmemD1Stride = B2_TMEM_D1_STRIDE;   // D1 (A = hi) is double buffered: columns 0..143 and 160..303
+constexpr uint32_t kTmemD2Col = B2_TMEM_D2_COL;         // D2 (A = lo): columns 320..463, accumulates for the whole kernel
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=144, M=128 (cute::UMMA::InstrDescriptor layout)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |

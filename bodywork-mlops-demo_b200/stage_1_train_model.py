@@ -63,15 +63,28 @@ def download_latest_dataset(bucket_dir: str) -> Tuple[pd.DataFrame, date]:
     folder = os.path.join(bucket_dir, "datasets")
     log.info(f"loading all available training data from {folder}")
     try:
-        keys = [k for k in sorted(os.listdir(folder)) if _DATE_RE.search(k) and k.endswith(".csv")]
+        keys = [k for k in sorted(os.listdir(folder)) if _DATE_RE.search(k) and k.endswith((".csv", ".b2t"))]
         if not keys:
-            raise FileNotFoundError("no regression-dataset-*.csv tranche found")
+            raise FileNotFoundError("no regression-dataset-* tranche found")
         dated = sorted(((k, _date_from_key(k)) for k in keys), key=lambda e: e[1])
-        dataset = pd.concat(pd.read_csv(os.path.join(folder, k)) for k, _ in dated)
+        dataset = pd.concat(_read_tranche_frame(os.path.join(folder, k)) for k, _ in dated)
     except OSError as e:
         log.error(e)
         raise RuntimeError(f"failed to load training data from {folder}")
     return dataset, dated[-1][1]
+
+
+def _read_tranche_frame(path: str) -> pd.DataFrame:
+    """A tranche as a DataFrame: the reference's CSV, or the binary row-major format of tranche_io."""
+    if path.endswith(".csv"):
+        return pd.read_csv(path)
+    from . import tranche_io
+    X, y, kind, day = tranche_io.read_tranche(path)
+    if kind != "f32":
+        X = native.from_bf16_bits(X)
+    cols = {"date": str(day), "y": y}
+    cols.update({("X" if X.shape[1] == 1 else f"X{j}"): X[:, j] for j in range(X.shape[1])})
+    return pd.DataFrame(cols)
 
 
 def feature_columns(data: pd.DataFrame) -> List[str]:

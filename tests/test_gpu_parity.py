@@ -353,3 +353,65 @@ def test_baseline_config_10m_x_128_properties(ctx, kind):
     assert _rel(tc, ref) < 2e-6
     for a in (X, y, Xs, ys):
         a.free()
+
+
+# ------------------------------------------------------------------------------------------------
+# 30-day concept-drift replay (BASELINE.json configs[4]); binary tranches through the stage
+# ------------------------------------------------------------------------------------------------
+def _drift_tranches(days, n, d, dtype=np.float32):
+    out = []
+    for day in range(days):
+        X, y = orc.generate_dataset(n, d, seed=500 + day, alpha=orc.alpha_of_day(1 + 7 * day), dtype=dtype,
+                                    drop_negative=(d == 1))
+        out.append((X, y))
+    return out
+
+
+@pytest.mark.parametrize("n,d,days", [(1440, 1, 30), (50_000, 128, 6)])
+def test_replay_incremental_equals_refit_on_the_same_train_rows(ctx, n, d, days):
+    from bodywork_mlops_demo_b200 import incremental
+    tranches = _drift_tranches(days, n, d)
+    res = incremental.replay(tranches, d, mode="incremental", ctx=ctx)
+    assert len(res) == days and res[0].test_mape is None and res[1].test_mape is not None
+    Xs, ys = [], []
+    for k, (X, y) in enumerate(tranches):
+        m = s1.split_mask(len(y))
+        Xs.append(X[m == 1]); ys.append(y[m == 1])
+        fo = orc.fit_lstsq(np.concatenate(Xs).astype(np.float64), np.concatenate(ys).astype(np.float64))
+        assert res[k].n_train_total == sum(len(v) for v in ys)
+        assert np.max(np.abs(res[k].coef - fo["coef"])) < COEF_TOL, k
+        if k + 1 < days:   # day k+1's tranche scored with model(k): stage_4 semantics
+            Xn, yn = tranches[k + 1]
+            mo = orc.metrics(yn, orc.predict(Xn, fo["coef"], fo["intercept"]))
+            assert res[k + 1].test_r2 == pytest.approx(mo["r_squared"], rel=1e-3, abs=1e-4)
+            assert res[k + 1].test_max_residual == pytest.approx(mo["max_residual"], rel=1e-3)
+
+
+def test_replay_exact_mode_reproduces_the_reference_split(ctx):
+    from bodywork_mlops_demo_b200 import incremental
+    tranches = _drift_tranches(5, 3000, 8)
+    res = incremental.replay(tranches, 8, mode="exact", ctx=ctx)
+    allX = np.concatenate([t[0] for t in tranches]); ally = np.concatenate([t[1] for t in tranches])
+    o = orc.train_model(allX, ally)            # the reference's global RandomState(42) split over all history
+    assert res[-1].n_train_total == o["n_train"]
+    assert np.max(np.abs(res[-1].coef - o["coef"])) < COEF_TOL
+
+
+def test_stage_reads_binary_tranches(tmp_path, monkeypatch):
+    import datetime as dt
+    import joblib
+    from bodywork_mlops_demo_b200 import tranche_io as tio
+    bucket = tmp_path / "bucket"
+    (bucket / "datasets").mkdir(parents=True)
+    Xs, ys = [], []
+    for k in range(3):
+        X, y = orc.generate_dataset(40_000, 16, seed=70 + k, dtype=np.float32)
+        tio.write_tranche(str(bucket / "datasets" / f"regression-dataset-2021-05-0{k + 1}.b2t"), X, y,
+                          dt.date(2021, 5, k + 1))
+        Xs.append(X); ys.append(y)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(s1, "BUCKET_DIR", str(bucket))
+    assert s1.run() == 0
+    model = joblib.load(bucket / "models" / "regressor-2021-05-03.joblib")
+    o = orc.train_model(np.concatenate(Xs), np.concatenate(ys))
+    assert np.max(np.abs(model.coef_ - o["coef"])) < COEF_TOL and model.n_features_in_ == 16
