@@ -43,12 +43,13 @@ constexpr int kThreads = 32 * (8 + kXformWarps);  // warps: 0 TMA, 1 MMA(+TMEM a
 constexpr int kProducers = kXformWarps + 1;        // warps that fill an operand stage (transform + E)
 constexpr int kKGroups = kTcRows / 8;              // 8-row K groups per stage
 constexpr uint32_t kRawStageBytes = kTcRows * kMaxD * 4;      // 32768 (fp32, D = 128)
-constexpr uint32_t kGroupsPerK = 16 + 2 + 16;                 // hi | E | lo groups of 8 j-rows
 constexpr uint32_t kOpSBO = 128;                              // bytes between 8-row j groups (core matrices along M/N)
-constexpr uint32_t kOpLBO = kGroupsPerK * kOpSBO;             // 4352: bytes between K groups (core matrices along K)
+constexpr uint32_t kOpLBO_SS = (16 + 2 + 16) * kOpSBO;        // 4352: hi | E | lo groups per K group (operands all in smem)
+constexpr uint32_t kOpLBO_TS = (16 + 2) * kOpSBO;             // 2304: hi | E only; A = lo is staged in TMEM (D = 128 path)
 constexpr uint32_t kOpEOff = 16 * kOpSBO;                     // E block inside a K group
-constexpr uint32_t kOpLoOff = 18 * kOpSBO;                    // lo block inside a K group
-constexpr uint32_t kOpStageBytes = kKGroups * kOpLBO;         // 34816
+constexpr uint32_t kOpLoOff = 18 * kOpSBO;                    // lo block inside a K group (SS layout only)
+constexpr uint32_t kOpStageBytes = kKGroups * kOpLBO_SS;      // 34816 (sized for the SS layout)
+constexpr uint32_t kTmemALoCol = 432;                         // TS: A = lo operand, 2 stages x 32 columns (432..495)
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;     // 131072
 constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;         // 200704
@@ -59,14 +60,8 @@ constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
 constexpr uint32_t kSmemBytes = kOffShift + (kMaxD + 4) * 4 + 1024;    // + alignment slack (~204 KB)
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-#ifndef B2_TMEM_D1_STRIDE
-#define B2_TMEM_D1_STRIDE 160
-#endif
-#ifndef B2_TMEM_D2_COL
-#define B2_TMEM_D2_COL 320
-#endif
-constexpr uint32_t kTmemD1Stride = B2_TMEM_D1_STRIDE;   // D1 (A = hi) is double buffered: columns 0..143 and 160..303
-constexpr uint32_t kTmemD2Col = B2_TMEM_D2_COL;         // D2 (A = lo): columns 320..463, accumulates for the whole kernel
+constexpr uint32_t kTmemD1Stride = 144;   // D1 (A = hi) is double buffered: columns 0..143 and 144..287
+constexpr uint32_t kTmemD2Col = 288;      // D2 (A = lo): columns 288..431, accumulates for the whole kernel
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=144, M=128 (cute::UMMA::InstrDescriptor layout)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
@@ -139,8 +134,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(kOpLBO >> 4) << 16) |
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) |
          ((uint64_t)(kOpSBO >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -151,6 +146,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (128 lanes x 8 columns of packed bf16 pairs per K = 16)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -260,6 +270,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                int64_t n_rows, int d_arg, const float* __restrict__ shift, int chunk_tiles,
                double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg) {
   const int d = DFIX ? DFIX : d_arg;
+  constexpr bool kTS = (DFIX == 128);                         // A = lo from TMEM (needs warp%4 == feature quad)
+  constexpr uint32_t kLBO = kTS ? kOpLBO_TS : kOpLBO_SS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -303,7 +315,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmY);
     if (has_mask) tma_prefetch_desc(&tmM);
   }
-  if (warp == 1) {  // TMEM: 512 columns (D1 x2 at 0 / 160, D2 at 320)
+  if (warp == 1) {  // TMEM: 512 columns (D1 x2 at 0 / 144, D2 at 288, TS operand A = lo at 432)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + kOffTmemPtr)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -356,10 +368,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const uint32_t tmem_d1 = tmem_base + (uint32_t)b * kTmemD1Stride;
 #pragma unroll
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint64_t b_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO);               // [hi | E], also A = hi
-          const uint64_t lo_desc = make_smem_desc(op_addr + k2 * 2 * kOpLBO + kOpLoOff);   // A = lo
+          const uint64_t b_desc = make_smem_desc(op_addr + k2 * 2 * kLBO, kLBO);            // [hi | E], also A = hi
           if (!(dbg & 2u)) umma_bf16(tmem_d1, b_desc, b_desc, (in_chunk > 0 || k2 > 0) ? 1u : 0u);
-          if (!(dbg & 3u)) umma_bf16(tmem_base + kTmemD2Col, lo_desc, b_desc, (it > 0 || k2 > 0) ? 1u : 0u);
+          if (!(dbg & 3u)) {
+            if constexpr (kTS) {
+              umma_bf16_ts(tmem_base + kTmemD2Col, tmem_base + kTmemALoCol + (uint32_t)(os * 32 + k2 * 8), b_desc,
+                           (it > 0 || k2 > 0) ? 1u : 0u);
+            } else {
+              const uint64_t lo_desc = make_smem_desc(op_addr + k2 * 2 * kLBO + kOpLoOff, kLBO);   // A = lo
+              umma_bf16(tmem_base + kTmemD2Col, lo_desc, b_desc, (it > 0 || k2 > 0) ? 1u : 0u);
+            }
+          }
         }
         umma_commit(bar_op_empty + 8 * os);  // frees the operand stage when these MMAs retire
         const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
@@ -393,7 +412,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const float yv = use ? ld_shared_f32(y_addr + rr * 4) - c_y : 0.f;
         uint32_t yh, yl;
         split2(yv, 0.f, yh, yl);
-        const uint32_t dst = e_addr + (rr >> 3) * kOpLBO + (rr & 7) * 2;
+        const uint32_t dst = e_addr + (rr >> 3) * kLBO + (rr & 7) * 2;
         st_shared_u16(dst, use ? 0x3F80u : 0u);   // bf16(1.0)
         st_shared_u16(dst + 16, yh);
         st_shared_u16(dst + 32, yl);
@@ -481,7 +500,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc[s] = shift_s[tv[s] ? i : 0];
       tr0[s] = g * 8;
       tsrc[s] = (uint32_t)(g * 8) * pitch + (uint32_t)(tv[s] ? i : 0) * esz;
-      tdst[s] = (uint32_t)g * kOpLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
+      tdst[s] = (uint32_t)g * kLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
     }
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
@@ -518,9 +537,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
           if (!(dbg & 4u)) {
             st_shared_v4(op_addr + tdst[s], hp);
-            st_shared_v4(op_addr + tdst[s] + kOpLoOff, lp);
+            if constexpr (kTS) {
+              // lane l of this warp owns TMEM lane 32*(warp%4)+l == feature i; K group g -> 4 packed columns
+              tmem_st4(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemALoCol +
+                           (uint32_t)(os * 32 + (tr0[s] >> 3) * 4), lp);
+            } else {
+              st_shared_v4(op_addr + tdst[s] + kOpLoOff, lp);
+            }
           }
         }
+      }
+      if constexpr (kTS) {
+        tmem_st_wait();
+        tc_fence_before();
       }
       if (!(dbg & 32u)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
