@@ -310,7 +310,8 @@ class Context:
     # -- scoring ------------------------------------------------------------------------------------------
     def score(self, X, coef: np.ndarray, intercept: float, y=None, row_mask=None, mask_keep: int = 1,
               want_yhat: bool = True):
-        """Returns (yhat | None, stats | None); stats = [sum_ape, sse, sum_y, sum_yy, max_abs_res, rows]."""
+        """Returns (yhat | None, stats | None); stats = the ten reductions of include/b2gram.h b2_score
+        ([sum_ape, sse, sum_y, sum_yy, max_abs_res, rows, sum_p, sum_pp, sum_yp, max_ape])."""
         ptr, xdt, mk, n, d = _x_kind(X)
         coef = np.ascontiguousarray(coef, dtype=np.float64).ravel()
         if coef.size != d:
@@ -322,7 +323,7 @@ class Context:
         if want_yhat:
             yhat = self.empty((n,), "f32") if mk == MEM_DEVICE else np.empty(n, dtype=np.float32)
             yhat_ptr = yhat.ptr if mk == MEM_DEVICE else yhat.ctypes.data
-        stats = np.zeros(6, dtype=np.float64) if y is not None else None
+        stats = np.zeros(10, dtype=np.float64) if y is not None else None
         _check(load().b2_score(self._h, ptr, xdt, n, d, d, mk, coef.ctypes.data, float(intercept), yp, mp,
                                int(mask_keep), yhat_ptr, stats.ctypes.data if stats is not None else None),
                "b2_score")

@@ -194,11 +194,13 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_red), sizeof(double) * (kTcAccElems + 16)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->shift), sizeof(float) * 64 * (kMaxD + 1)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->simt_part), sizeof(double) * (size_t)ctx->simt_ctas * kMaxS * kMaxS));
-  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->score_part), sizeof(double) * ((size_t)ctx->score_ctas + 1) * 6));
+  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->score_part), sizeof(double) * ((size_t)ctx->score_ctas + 2) * 10));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->coef_dev), sizeof(double) * (kMaxD + 1)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->solve_out), sizeof(double) * (2 * kMaxD + 8)));
+  B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->solve_host), sizeof(double) * (2 * kMaxD + 8), cudaHostAllocDefault));
   B2_CUDA(cudaMemset(ctx->S, 0, sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMemset(ctx->tc_side, 0, sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
+  B2_CUDA(cudaMemset(ctx->tc_red, 0, sizeof(double) * (kTcAccElems + 16)));   // incl. the finalize ticket
   *out = ctx;
   return B2_OK;
 }
@@ -212,6 +214,7 @@ int b2_ctx_destroy(b2_ctx* ctx) {
                   ctx->coef_dev, ctx->solve_out, ctx->stage_x[0], ctx->stage_x[1], ctx->stage_y[0], ctx->stage_y[1],
                   ctx->stage_m[0], ctx->stage_m[1]};
   for (void* p : bufs) if (p != nullptr) cudaFree(p);
+  if (ctx->solve_host != nullptr) cudaFreeHost(ctx->solve_host);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
@@ -369,8 +372,8 @@ int b2_gram_import(b2_ctx* ctx, const double* S_in, int d) {
 
 // ---- solve ------------------------------------------------------------------------------------------
 static int fetch_solution(b2_ctx* ctx, double* coef, double* intercept, double* singular, int* rank, double* info) {
-  double host[2 * kMaxD + 8];
-  B2_CUDA(cudaMemcpyAsync(host, ctx->solve_out, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+  double* host = ctx->solve_host;
+  B2_CUDA(cudaMemcpyAsync(host, ctx->solve_out, sizeof(double) * (2 * kMaxD + 8), cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   if (coef != nullptr) memcpy(coef, host, sizeof(double) * ctx->d);
   if (intercept != nullptr) *intercept = host[kMaxD];
@@ -421,9 +424,9 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
   cbuf[kMaxD] = intercept;
   B2_CUDA(cudaMemcpyAsync(ctx->coef_dev, cbuf, sizeof(cbuf), cudaMemcpyHostToDevice, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));  // cbuf is on this stack frame
-  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 6;
+  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 10;
   if (n_rows == 0) {
-    B2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 6, ctx->stream));
+    B2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 10, ctx->stream));
   } else if (mem_kind == B2_MEM_DEVICE) {
     if (int r = launch_score(ctx, X, x_dtype, n_rows, d, ldx, y, row_mask, mask_keep, yhat, true)) return r;
   } else {
@@ -458,7 +461,7 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
     B2_CUDA(cudaGetLastError());
   }
   if (stats_out != nullptr && y != nullptr) {
-    B2_CUDA(cudaMemcpyAsync(stats_out, acc, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaMemcpyAsync(stats_out, acc, sizeof(double) * 10, cudaMemcpyDeviceToHost, ctx->stream));
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return B2_OK;
@@ -470,19 +473,22 @@ int b2_score_allreduce(b2_ctx* ctx, double* stats) {
   if (ctx->n_ranks == 1 || ctx->comm == nullptr) return B2_OK;
   NcclApi* api = nccl();
   if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
-  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 6;
-  double* mx = ctx->score_part;  // scratch slot for the max
-  double host[6];
+  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 10;   // 10 sums
+  double* mx = acc + 10;                                          // 2 maxima
+  double host[10], hmax[2];
   memcpy(host, stats, sizeof(host));
-  const double hmax = host[4];
-  host[4] = 0.0;
+  hmax[0] = host[4]; hmax[1] = host[9];
+  host[4] = 0.0; host[9] = 0.0;
   B2_CUDA(cudaMemcpyAsync(acc, host, sizeof(host), cudaMemcpyHostToDevice, ctx->stream));
-  B2_CUDA(cudaMemcpyAsync(mx, &hmax, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  B2_NCCL(api, api->AllReduce(acc, acc, 6, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
-  B2_NCCL(api, api->AllReduce(mx, mx, 1, kNcclFloat64, kNcclMax, ctx->comm, ctx->stream));
-  B2_CUDA(cudaMemcpyAsync(stats, acc, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
-  B2_CUDA(cudaMemcpyAsync(stats + 4, mx, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(mx, hmax, sizeof(hmax), cudaMemcpyHostToDevice, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));   // host / hmax live on this stack frame
+  B2_NCCL(api, api->AllReduce(acc, acc, 10, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
+  B2_NCCL(api, api->AllReduce(mx, mx, 2, kNcclFloat64, kNcclMax, ctx->comm, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(host, acc, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaMemcpyAsync(hmax, mx, sizeof(hmax), cudaMemcpyDeviceToHost, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  host[4] = hmax[0]; host[9] = hmax[1];
+  memcpy(stats, host, sizeof(host));
   return B2_OK;
 }
 

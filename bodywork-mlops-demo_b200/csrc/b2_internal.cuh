@@ -60,6 +60,14 @@ struct b2_ctx {
   double* tc_red = nullptr;            // [kTcAccElems + 8] reduced over CTAs
   float* shift = nullptr;              // [64][kMaxD + 1] partial sums of the row sample -> per-column shift c
   bool tc_attr_set = false;
+  bool solve_attr_set = false;
+  double* solve_host = nullptr;        // pinned mirror of solve_out (D2H without a staging copy)
+  // tensor-map cache of the most recent tcgen05 launch (a refit of resident rows re-uses the same maps)
+  struct TmCache {
+    const void* X = nullptr; const float* y = nullptr; const uint8_t* mask = nullptr;
+    int64_t n = 0, ldx = 0; int d = 0, x_dtype = -1, y_map_2d = 0;
+    alignas(64) unsigned char tmX[128], tmY[128], tmM[128];
+  } tm_cache;
   // SIMT path scratch
   double* simt_part = nullptr;         // [simt_ctas][kMaxS*kMaxS]
   int simt_ctas = 0;

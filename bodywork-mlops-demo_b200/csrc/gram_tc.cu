@@ -23,8 +23,8 @@
 // the centring in the solve subtracts almost nothing.  hi+lo carries 16 mantissa bits, i.e. products are
 // accurate to ~2^-17 relative (lo*lo is dropped).
 //
-// The finalize kernels reduce the per-CTA partials in a fixed order (deterministic), undo the shift in
-// fp64 and add the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
+// tc_finalize_kernel reduces the per-CTA partials in a fixed order (deterministic), and its last block undoes
+// the shift in fp64 and adds the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -573,33 +573,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// finalize 1: reduce the per-CTA partials in CTA order (deterministic)
+// finalize (one launch): every block reduces a slice of the per-CTA partials in CTA order (deterministic)
 //   red[col * 128 + i], col in [0, 288):  col < 144: D1 (A = hi), col >= 144: D2 (A = lo), columns of [hi | E]
 //   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
+// and the last block to finish (atomic ticket) undoes the shift in fp64 and adds the result into the raw
+// statistic S ((d+2)^2, row stride d+2).
 // ------------------------------------------------------------------------------------------
-__global__ void tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
-                                 double* __restrict__ red) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < kTcAccElems) {
-    double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) s += part[(size_t)c * kTcAccElems + idx];
-    red[idx] = s;
-  } else if (idx < kTcAccElems + 3) {
-    const int k = idx - kTcAccElems;
-    double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k];
-    red[idx] = s;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// finalize 2: undo the shift in fp64 and add into the raw statistic S ((d+2)^2, row stride d+2)
-// ------------------------------------------------------------------------------------------
-__global__ void tc_fold_kernel(const double* __restrict__ red, const float* __restrict__ shift, int64_t n_rows,
-                               int d, double* __restrict__ S) {
+__device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, const double* __restrict__ c,
+                                                int d, int idx, double* __restrict__ S) {
   const int dp = d + 2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= dp * dp) return;
   const int a = idx / dp, b = idx % dp;
   // D1[i][j] = red[j*128 + i], D2[i][j] = red[(144 + j)*128 + i]
   auto D1 = [&](int i, int j) { return red[(size_t)j * kTcM + i]; };
@@ -609,10 +591,10 @@ __global__ void tc_fold_kernel(const double* __restrict__ red, const float* __re
   const double sy = red[kTcAccElems + 0];
   const double syy = red[kTcAccElems + 1];
   const double n = red[kTcAccElems + 2];
-  const double cy = (double)shift_value(shift, kMaxD, n_rows);
+  const double cy = c[kMaxD];
   double val;
   if (a < d && b < d) {
-    const double ca = (double)shift_value(shift, a, n_rows), cb = (double)shift_value(shift, b, n_rows);
+    const double ca = c[a], cb = c[b];
     // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hi.hi + lo.hi + hi.lo   (lo.lo dropped, ~2^-18 relative)
     const double hh = 0.5 * (D1(a, b) + D1(b, a));
     const double hl = D2(a, b) + D2(b, a);
@@ -620,7 +602,7 @@ __global__ void tc_fold_kernel(const double* __restrict__ red, const float* __re
   } else if (a < d || b < d) {
     const int i = a < d ? a : b;
     const int o = a < d ? b : a;  // d (ones) or d+1 (y)
-    const double ci = (double)shift_value(shift, i, n_rows);
+    const double ci = c[i];
     if (o == d) val = s1(i) + n * ci;
     else val = sxy(i) + cy * s1(i) + ci * sy + n * ci * cy;
   } else if (a == d && b == d) {
@@ -631,6 +613,48 @@ __global__ void tc_fold_kernel(const double* __restrict__ red, const float* __re
     val = sy + n * cy;
   }
   S[idx] += val;
+}
+
+constexpr int kFinalizeThreads = 256;
+
+__global__ void __launch_bounds__(kFinalizeThreads)
+tc_finalize_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
+                   double* __restrict__ red, const float* __restrict__ shift, int64_t n_rows, int d,
+                   double* __restrict__ S, unsigned int* __restrict__ ticket) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < kTcAccElems) {
+    double s0 = 0.0, s1 = 0.0;                       // two chains: the loads are the latency
+    int c = 0;
+    for (; c + 1 < n_ctas; c += 2) {
+      s0 += part[(size_t)c * kTcAccElems + idx];
+      s1 += part[(size_t)(c + 1) * kTcAccElems + idx];
+    }
+    if (c < n_ctas) s0 += part[(size_t)c * kTcAccElems + idx];
+    red[idx] = s0 + s1;
+  } else if (idx < kTcAccElems + 3) {
+    const int k = idx - kTcAccElems;
+    double s = 0.0;
+    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k];
+    red[idx] = s;
+  }
+  // ---- last block folds ----------------------------------------------------------------------
+  __shared__ bool is_last;
+  __shared__ double c_s[kMaxD + 1];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;                        // re-arm for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
+    c_s[j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
+  __syncthreads();
+  const int dp = d + 2;
+  for (int e = threadIdx.x; e < dp * dp; e += blockDim.x) tc_fold_element(red, c_s, d, e, S);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -662,15 +686,10 @@ bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, in
   return true;
 }
 
-int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
-                   const uint8_t* mask, int keep) {
-  PFN_encodeTiled encode = get_encode();
-  if (encode == nullptr) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return B2_E_CUDA;
-  }
-  const int es = x_dtype == B2_F32 ? 4 : 2;
-  CUtensorMap tmX, tmY, tmM;
+static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int es, const float* y, int64_t n, int d,
+                       int64_t ldx, const uint8_t* mask, CUtensorMap* tmX_out, CUtensorMap* tmY_out,
+                       CUtensorMap* tmM_out, int* y_map_2d_out) {
+  CUtensorMap& tmX = *tmX_out; CUtensorMap& tmY = *tmY_out; CUtensorMap& tmM = *tmM_out;
   memset(&tmM, 0, sizeof(tmM));
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
@@ -730,6 +749,32 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     }
   }
 
+  *y_map_2d_out = y_map_2d;
+  return B2_OK;
+}
+
+int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
+                   const uint8_t* mask, int keep) {
+  PFN_encodeTiled encode = get_encode();
+  if (encode == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return B2_E_CUDA;
+  }
+  const int es = x_dtype == B2_F32 ? 4 : 2;
+  CUtensorMap tmX, tmY, tmM;
+  int y_map_2d = 0;
+  b2_ctx::TmCache& tc = ctx->tm_cache;
+  const bool cached = tc.X == X && tc.y == y && tc.mask == mask && tc.n == n && tc.ldx == ldx && tc.d == d &&
+                      tc.x_dtype == x_dtype;
+  if (cached) {
+    memcpy(&tmX, tc.tmX, sizeof(tmX)); memcpy(&tmY, tc.tmY, sizeof(tmY)); memcpy(&tmM, tc.tmM, sizeof(tmM));
+    y_map_2d = tc.y_map_2d;
+  } else {
+    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d, ldx, mask, &tmX, &tmY, &tmM, &y_map_2d)) return r;
+    tc.X = X; tc.y = y; tc.mask = mask; tc.n = n; tc.ldx = ldx; tc.d = d; tc.x_dtype = x_dtype; tc.y_map_2d = y_map_2d;
+    memcpy(tc.tmX, &tmX, sizeof(tmX)); memcpy(tc.tmY, &tmY, sizeof(tmY)); memcpy(tc.tmM, &tmM, sizeof(tmM));
+  }
+
   const int64_t total_tiles = (n + kTcRows - 1) / kTcRows;
   const int grid = (int)(total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count);
   int chunk_tiles = ctx->drain_rows / kTcRows;
@@ -778,13 +823,12 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   ctx->k_pairs += 1;
 
   const int red_elems = kTcAccElems + 3;
-  tc_reduce_kernel<<<(red_elems + 255) / 256, 256, 0, ctx->stream>>>(ctx->tc_part, ctx->tc_side, grid, ctx->tc_red);
+  tc_finalize_kernel<<<(red_elems + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
+      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n, d, ctx->S,
+      reinterpret_cast<unsigned int*>(ctx->tc_red + kTcAccElems + 12));
   B2_CUDA(cudaGetLastError());
-  const int dp = d + 2;
-  tc_fold_kernel<<<(dp * dp + 255) / 256, 256, 0, ctx->stream>>>(ctx->tc_red, ctx->shift, n, d, ctx->S);
-  B2_CUDA(cudaGetLastError());
-  ctx->launches += 4;
-  ctx->k_launches += 4;
+  ctx->launches += 3;
+  ctx->k_launches += 3;
   return B2_OK;
 }
 

@@ -19,18 +19,24 @@ constexpr int kScoreThreads = 256;
 constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr double kEpsF64 = 2.220446049250313e-16;
 
+constexpr int kNStats = 10;   // include/b2gram.h: b2_score stats_out layout
 struct RowStats {
-  double ape = 0.0, sse = 0.0, sy = 0.0, syy = 0.0, mx = 0.0, cnt = 0.0;
+  double ape = 0.0, sse = 0.0, sy = 0.0, syy = 0.0, mx = 0.0, cnt = 0.0, sp = 0.0, spp = 0.0, syp = 0.0, mxape = 0.0;
   __device__ void add(double y, double p) {
     const double e = fabs(p - y);
-    ape += e / fmax(fabs(y), kEpsF64);
+    ape += e / fmax(fabs(y), kEpsF64);            // sklearn MAPE term (stage_1_train_model.py:81)
     sse += (y - p) * (y - p);
     sy += y;
     syy += y * y;
     mx = fmax(mx, e);
     cnt += 1.0;
+    sp += p;                                      // Pearson correlation terms (stage_4...:103 "r_squared")
+    spp += p * p;
+    syp += y * p;
+    mxape = fmax(mxape, e / fabs(y));             // |score/label - 1| (stage_4...:89,104); inf when label == 0
   }
 };
+__device__ __forceinline__ bool stat_is_max(int k) { return k == 4 || k == 9; }
 
 template <typename T>
 __device__ __forceinline__ double lane_dot(const T* __restrict__ row, int d, int lane, const double* cf, bool vec);
@@ -123,31 +129,33 @@ score_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const doubl
       }
     }
   }
-  __shared__ double red[kScoreWarps][6];
+  __shared__ double red[kScoreWarps][kNStats];
   if (lane == 0) {
-    red[warp][0] = st.ape; red[warp][1] = st.sse; red[warp][2] = st.sy;
-    red[warp][3] = st.syy; red[warp][4] = st.mx;  red[warp][5] = st.cnt;
+    red[warp][0] = st.ape; red[warp][1] = st.sse; red[warp][2] = st.sy;  red[warp][3] = st.syy; red[warp][4] = st.mx;
+    red[warp][5] = st.cnt; red[warp][6] = st.sp;  red[warp][7] = st.spp; red[warp][8] = st.syp; red[warp][9] = st.mxape;
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
+  if (threadIdx.x < kNStats) {
+    const int k = threadIdx.x;
     double v = 0.0;
-    for (int w = 0; w < kScoreWarps; ++w) v = (threadIdx.x == 4) ? fmax(v, red[w][4]) : v + red[w][threadIdx.x];
-    part[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+    for (int w = 0; w < kScoreWarps; ++w) v = stat_is_max(k) ? fmax(v, red[w][k]) : v + red[w][k];
+    part[(size_t)blockIdx.x * kNStats + k] = v;
   }
 }
 
 // acc[0..5] (at part + n_ctas*6 ... see launch) = combine over CTAs in order; `first` overwrites.
 __global__ void score_reduce_kernel(const double* __restrict__ part, int n_ctas, int first, double* __restrict__ acc) {
   const int k = threadIdx.x;
-  if (k >= 6) return;
+  if (k >= kNStats) return;
   double v = first ? 0.0 : acc[k];
-  for (int c = 0; c < n_ctas; ++c) v = (k == 4) ? fmax(v, part[(size_t)c * 6 + 4]) : v + part[(size_t)c * 6 + k];
+  for (int c = 0; c < n_ctas; ++c)
+    v = stat_is_max(k) ? fmax(v, part[(size_t)c * kNStats + k]) : v + part[(size_t)c * kNStats + k];
   acc[k] = v;
 }
 
 }  // namespace
 
-// ctx->score_part layout: [score_ctas][6] partials, then 6 doubles of running totals.
+// ctx->score_part layout: [score_ctas][10] partials, then 10 doubles of running totals.
 int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx, const float* y,
                  const uint8_t* mask, int keep, float* yhat, bool first_block) {
   const int es = x_dtype == B2_F32 ? 4 : 2;
@@ -155,7 +163,7 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
   int64_t want = (n + kScoreWarps * 4 - 1) / (kScoreWarps * 4);
   if (want < 1) want = 1;
   const int grid = (int)(want < ctx->score_ctas ? want : ctx->score_ctas);
-  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 6;
+  double* acc = ctx->score_part + (size_t)ctx->score_ctas * kNStats;
   if (x_dtype == B2_F32)
     score_kernel<float><<<grid, kScoreThreads, 0, ctx->stream>>>(static_cast<const float*>(X), n, d, ldx,
                                                                  ctx->coef_dev, y, mask, keep, yhat, vec,

@@ -183,28 +183,39 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
     __syncthreads();
     tm[2] += clock64() - tc0; tc0 = clock64();
     // ---- (3) trailing update A[i][j] -= sum_m P[i][m] P[j][m], i >= j >= kb+nb (i up to the r row) -----------
-    const int ty = tid >> 4, tx = tid & 15;           // 32 x 16 thread tile
+    // each thread owns a 2-row x 4-column register tile: 8 independent fp64 chains, one shared-memory load per
+    // two FMAs (the panel rows P[i][.] stay in registers)
+    const int ty = tid >> 4, tx = tid & 15;           // 32 x 16 thread grid
     const int base = kb + nb;
-    for (int i = base + ty; i < rows; i += kCholThreads / 16) {
-      double pi[kNB];
+    for (int i0 = base + ty; i0 < rows; i0 += 64) {
+      const int i1 = i0 + 32;
+      const bool has1 = i1 < rows;
+      double p0[kNB], p1[kNB];
 #pragma unroll
-      for (int m = 0; m < kNB; ++m) pi[m] = m < nb ? A[i * pitch + kb + m] : 0.0;
-      const int jmax = i < d ? i : d - 1;
-      for (int j0 = base + tx; j0 <= jmax; j0 += 64) {   // 4 columns (stride 16) per pass: independent chains
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int m = 0; m < kNB; ++m) {
+        p0[m] = m < nb ? A[i0 * pitch + kb + m] : 0.0;
+        p1[m] = (m < nb && has1) ? A[i1 * pitch + kb + m] : 0.0;
+      }
+      const int jmax0 = i0 < d ? i0 : d - 1;
+      const int jmax1 = has1 ? (i1 < d ? i1 : d - 1) : -1;
+      const int jmax = jmax1 > jmax0 ? jmax1 : jmax0;
+      for (int j0 = base + tx; j0 <= jmax; j0 += 64) {
+        double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int m = 0; m < kNB; ++m) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = j0 + 16 * u;
             const double pj = (m < nb && j <= jmax) ? A[j * pitch + kb + m] : 0.0;
-            acc[u] = fma(pi[m], pj, acc[u]);
+            a0[u] = fma(p0[m], pj, a0[u]);
+            a1[u] = fma(p1[m], pj, a1[u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + 16 * u;
-          if (j <= jmax) A[i * pitch + j] -= acc[u];
+          if (j <= jmax0) A[i0 * pitch + j] -= a0[u];
+          if (j <= jmax1) A[i1 * pitch + j] -= a1[u];
         }
       }
     }
@@ -393,7 +404,13 @@ size_t solve_smem_bytes(int d) { return sizeof(double) * ((size_t)(d + 1) * (d +
 
 int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept) {
   const size_t smem = solve_smem_bytes(ctx->d);
-  B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!ctx->solve_attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(kMaxD)));
+    B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(kMaxD)));
+    ctx->solve_attr_set = true;
+  }
   solve_cholesky_kernel<<<1, kCholThreads, smem, ctx->stream>>>(ctx->S, ctx->d, alpha, fit_intercept,
                                                                  ctx->solve_out);
   B2_CUDA(cudaGetLastError());
@@ -403,7 +420,13 @@ int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept) {
 
 int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept) {
   const size_t smem = solve_smem_bytes(ctx->d);
-  B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (!ctx->solve_attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(kMaxD)));
+    B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)solve_smem_bytes(kMaxD)));
+    ctx->solve_attr_set = true;
+  }
   solve_spectral_kernel<<<1, 512, smem, ctx->stream>>>(ctx->S, ctx->d, cond, fit_intercept, ctx->solve_out);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 1;

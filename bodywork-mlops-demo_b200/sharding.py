@@ -2,7 +2,7 @@
 
 The statistic S = [X 1 y]^T [X 1 y] is a sum over rows, so any row partition works: rank r accumulates
 rows [lo, hi) and the only exchange is one all-reduce of (D+2)^2 doubles (b2_gram_allreduce).  Scoring shards
-the same way and combines six numbers (five sums, one max: b2_score_allreduce).
+the same way and combines ten numbers (eight sums, two maxima: b2_score_allreduce).
 """
 from __future__ import annotations
 
@@ -29,8 +29,9 @@ def all_shards(n_rows: int, world: int, align: int = TILE_ROWS) -> List[Tuple[in
 
 
 def combine_score_stats(parts: np.ndarray) -> np.ndarray:
-    """Combine per-rank [sum_ape, sse, sum_y, sum_yy, max_abs_res, rows] the way b2_score_allreduce does."""
-    parts = np.asarray(parts, dtype=np.float64).reshape(-1, 6)
+    """Combine per-rank score reductions (10 per rank) the way b2_score_allreduce does: sums, maxima at 4 and 9."""
+    parts = np.asarray(parts, dtype=np.float64).reshape(-1, 10)
     out = parts.sum(axis=0)
     out[4] = parts[:, 4].max()
+    out[9] = parts[:, 9].max()
     return out

@@ -113,8 +113,8 @@ def split_mask(n: int, test_size: float = 0.2, seed: int = 42) -> np.ndarray:
 
 
 def metrics_from_stats(stats: np.ndarray) -> Tuple[float, float, float]:
-    """(MAPE, r_squared, max_residual) from the six device reductions (include/b2gram.h, b2_score)."""
-    sum_ape, sse, sy, syy, mx, cnt = (float(v) for v in stats)
+    """(MAPE, r_squared, max_residual) from the device reductions (include/b2gram.h, b2_score: entries 0..5)."""
+    sum_ape, sse, sy, syy, mx, cnt = (float(v) for v in np.asarray(stats)[:6])
     if cnt < 1:
         raise RuntimeError("no rows were scored")
     mape = sum_ape / cnt

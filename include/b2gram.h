@@ -113,9 +113,12 @@ int b2_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept, double* coef,
  * reference: stage_1_train_model.py:107 / stage_2_serve_model.py:78 (X @ coef_ + intercept_)
  *            stage_1_train_model.py:79-90 (MAPE, r2_score, max_error)
  * yhat may be NULL (metrics only); y may be NULL (predict only; stats_out untouched).
- * stats_out (host, 6 doubles): [ sum |yhat-y|/max(|y|,eps_f64), sum (y-yhat)^2, sum y, sum y^2,
- *                               max |y-yhat|, rows used ]
- * With a communicator, b2_score_allreduce combines the six across ranks (sum x5 / max x1). */
+ * stats_out (host, 10 doubles):
+ *   [0] sum |yhat-y|/max(|y|,eps_f64)  [1] sum (y-yhat)^2  [2] sum y  [3] sum y^2  [4] max |y-yhat|  [5] rows used
+ *   [6] sum yhat  [7] sum yhat^2  [8] sum y*yhat  [9] max |yhat/y - 1|
+ *   ([0]-[5]: stage_1's model_metrics; [6]-[9]: stage_4_test_model_scoring_service.py:89,101-105 -- APE,
+ *    Pearson "r_squared", max APE.)
+ * With a communicator, b2_score_allreduce combines the ten across ranks (sums; [4] and [9] by max). */
 int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int64_t ldx,
              int mem_kind, const double* coef, double intercept, const float* y,
              const uint8_t* row_mask, int mask_keep, float* yhat, double* stats_out);

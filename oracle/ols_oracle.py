@@ -169,13 +169,26 @@ def metrics(y_actual: np.ndarray, y_predicted: np.ndarray) -> Dict[str, float]:
 
 
 def score_stats(y: np.ndarray, p: np.ndarray) -> np.ndarray:
-    """The five reductions the CUDA metrics kernel produces: [sum_ape, sse, sum_y, sum_yy, max_abs_res, n]."""
+    """The ten reductions the CUDA scoring kernel produces (include/b2gram.h, b2_score):
+    [sum_ape, sse, sum_y, sum_yy, max_abs_res, n, sum_p, sum_pp, sum_yp, max_ape]."""
     y = np.asarray(y, dtype=np.float64)
     p = np.asarray(p, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        max_ape = np.max(np.abs(p - y) / np.abs(y)) if y.size else 0.0
     return np.array([
         np.sum(np.abs(p - y) / np.maximum(np.abs(y), F64_EPS)),
         np.sum((y - p) ** 2), np.sum(y), np.sum(y * y), np.max(np.abs(y - p)) if y.size else 0.0,
-        float(y.size)])
+        float(y.size), np.sum(p), np.sum(p * p), np.sum(y * p), max_ape])
+
+
+def service_test_metrics(label: np.ndarray, score: np.ndarray) -> Dict[str, float]:
+    """stage_4_test_model_scoring_service.py:86-90,101-105: APE = |score/label - 1|, MAPE = mean APE,
+    'r_squared' = Pearson correlation(score, label), 'max_residual' = max APE."""
+    label = np.asarray(label, dtype=np.float64)
+    score = np.asarray(score, dtype=np.float64)
+    ape = np.abs(score / label - 1.0)
+    return {"MAPE": float(ape.mean()), "r_squared": float(np.corrcoef(score, label)[0, 1]),
+            "max_residual": float(ape.max())}
 
 
 # --------------------------------------------------------------------------------------

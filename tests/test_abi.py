@@ -131,3 +131,21 @@ def test_feature_columns_and_dataset_loader(tmp_path):
     assert s1.feature_columns(pd.DataFrame({"y": [1], "X10": [1], "X2": [1]})) == ["X2", "X10"]
     with pytest.raises(RuntimeError):
         s1.download_latest_dataset(str(tmp_path / "missing"))
+
+
+def test_service_test_metrics_algebra_matches_stage_4_definitions():
+    """stage_4's record (APE mean, Pearson 'r_squared', max APE) from the ten reductions == direct evaluation."""
+    import datetime as dt
+    from bodywork_mlops_demo_b200 import stage_2_scoring as s2
+    rng = np.random.RandomState(3)
+    label = rng.uniform(5, 80, 1317)
+    score = label * (1 + rng.normal(0, 0.3, 1317))
+    rec = s2.test_metrics_from_stats(orc.score_stats(label, score), dt.date(2021, 4, 8), 0.00822)
+    want = orc.service_test_metrics(label, score)
+    assert list(rec.columns) == ["date", "MAPE", "r_squared", "max_residual", "mean_response_time"]
+    assert rec["MAPE"].iloc[0] == pytest.approx(want["MAPE"], rel=1e-12)
+    assert rec["r_squared"].iloc[0] == pytest.approx(want["r_squared"], rel=1e-10)
+    assert rec["max_residual"].iloc[0] == pytest.approx(want["max_residual"], rel=1e-12)
+    import pandas as pd
+    df = pd.DataFrame({"score": score, "label": label})          # the reference's own pandas expressions
+    assert rec["r_squared"].iloc[0] == pytest.approx(df.score.corr(df.label), rel=1e-10)

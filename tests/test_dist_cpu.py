@@ -56,8 +56,8 @@ _WORKER = textwrap.dedent("""
     # scoring: five sums + one max
     p = orc.predict(X[lo:hi], fit["coef"], fit["intercept"])
     st = torch.from_numpy(orc.score_stats(y[lo:hi], p))
-    mx = st[4:5].clone(); st[4] = 0.0
-    dist.all_reduce(st, op=dist.ReduceOp.SUM); dist.all_reduce(mx, op=dist.ReduceOp.MAX); st[4] = mx[0]
+    mx = st[[4, 9]].clone(); st[4] = 0.0; st[9] = 0.0       # eight sums + two maxima (b2_score_allreduce)
+    dist.all_reduce(st, op=dist.ReduceOp.SUM); dist.all_reduce(mx, op=dist.ReduceOp.MAX); st[4] = mx[0]; st[9] = mx[1]
     # max-over-ranks timing rule used by bench.py
     t = torch.tensor([1.0 + rank], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -415,3 +415,41 @@ def test_stage_reads_binary_tranches(tmp_path, monkeypatch):
     model = joblib.load(bucket / "models" / "regressor-2021-05-03.joblib")
     o = orc.train_model(np.concatenate(Xs), np.concatenate(ys))
     assert np.max(np.abs(model.coef_ - o["coef"])) < COEF_TOL and model.n_features_in_ == 16
+
+
+# ------------------------------------------------------------------------------------------------
+# batch scoring companion of stage_2 + stage_4's service-test metrics
+# ------------------------------------------------------------------------------------------------
+def test_score_payload_follows_the_service_shape_rules(ctx):
+    from sklearn.linear_model import LinearRegression
+    from bodywork_mlops_demo_b200 import stage_2_scoring as s2
+    X, y = orc.generate_dataset(2000, 3, seed=6)
+    model = LinearRegression().fit(X, y)
+    for features in ([50.0, 2.0, 7.0], [[50.0, 2.0, 7.0], [1.0, 2.0, 3.0]]):
+        want = model.predict(np.array(features, ndmin=2))                  # stage_2_serve_model.py:77-78
+        got = s2.score_payload(model, {"X": features}, ctx)
+        assert got["prediction"] == pytest.approx(want[0], rel=1e-6)
+        np.testing.assert_allclose(got["predictions"], want, rtol=1e-6)
+        assert got["model_info"] == "LinearRegression()"
+    X1, y1 = orc.generate_dataset(500, 1, seed=8)
+    m1 = LinearRegression().fit(X1, y1)
+    assert s2.score_payload(m1, {"X": 50}, ctx)["prediction"] == pytest.approx(m1.predict(np.array(50, ndmin=2))[0],
+                                                                                    rel=1e-6)
+    with pytest.raises(ValueError):
+        s2.score_batch(model, [[1.0, 2.0]], ctx)
+
+
+@pytest.mark.parametrize("n,d", [(1317, 1), (200_000, 128)])
+def test_service_test_matches_stage_4_metric_definitions(ctx, n, d):
+    from sklearn.linear_model import LinearRegression
+    from bodywork_mlops_demo_b200 import stage_2_scoring as s2
+    X, y = orc.generate_dataset(n + 500, d, seed=9, dtype=np.float32, drop_negative=(d == 1))
+    model = LinearRegression().fit(X[:500].astype(np.float64), y[:500].astype(np.float64))
+    Xt, yt = X[500:], y[500:]
+    rec = s2.service_test(model, Xt, yt, ctx=ctx)
+    want = orc.service_test_metrics(yt.astype(np.float64), model.predict(Xt.astype(np.float64)))
+    assert rec["MAPE"].iloc[0] == pytest.approx(want["MAPE"], rel=1e-5)
+    assert rec["r_squared"].iloc[0] == pytest.approx(want["r_squared"], rel=1e-6)
+    assert rec["max_residual"].iloc[0] == pytest.approx(want["max_residual"], rel=1e-4)
+    assert rec["mean_response_time"].iloc[0] < 8.22e-3      # the reference's recorded 8.22 ms per row over HTTP
+    np.testing.assert_allclose(s2.score_batch(model, Xt, ctx), model.predict(Xt.astype(np.float64)), rtol=2e-6)
