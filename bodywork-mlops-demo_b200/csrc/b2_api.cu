@@ -191,7 +191,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->S), sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_part), sizeof(double) * (size_t)ctx->sm_count * kTcAccElems));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_side), sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
-  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_red), sizeof(double) * (kTcAccElems + 16)));
+  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_red), sizeof(double) * (kTcAccElems + 16 + kMaxD + 8)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->shift), sizeof(float) * 64 * (kMaxD + 1)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->simt_part), sizeof(double) * (size_t)ctx->simt_ctas * kMaxS * kMaxS));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->score_part), sizeof(double) * ((size_t)ctx->score_ctas + 2) * 10));
@@ -200,7 +200,7 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->solve_host), sizeof(double) * (2 * kMaxD + 8), cudaHostAllocDefault));
   B2_CUDA(cudaMemset(ctx->S, 0, sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMemset(ctx->tc_side, 0, sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
-  B2_CUDA(cudaMemset(ctx->tc_red, 0, sizeof(double) * (kTcAccElems + 16)));   // incl. the finalize ticket
+  B2_CUDA(cudaMemset(ctx->tc_red, 0, sizeof(double) * (kTcAccElems + 16 + kMaxD + 8)));
   *out = ctx;
   return B2_OK;
 }
@@ -389,11 +389,15 @@ int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double*
   if (!(alpha >= 0.0)) { set_error("alpha must be >= 0"); return B2_E_ARG; }
   if (int r = launch_solve_cholesky(ctx, alpha, fit_intercept)) return r;
   double info = 0.0;
+#ifdef B2_DEV_KNOBS
   double phase[kMaxD];
   if (int r = fetch_solution(ctx, coef, intercept, getenv("B2_SOLVE_TIMING") ? phase : nullptr, nullptr, &info)) return r;
   if (getenv("B2_SOLVE_TIMING"))
     fprintf(stderr, "[b2_solve] cycles: build %.0f diag %.0f panel %.0f update %.0f backward %.0f\n", phase[0], phase[1],
             phase[2], phase[3], phase[4]);
+#else
+  if (int r = fetch_solution(ctx, coef, intercept, nullptr, nullptr, &info)) return r;
+#endif
   if (info != 0.0) {
     set_error("Cholesky pivot %d is not positive: the centred Gram matrix is rank deficient "
               "(use alpha > 0 or b2_solve_spectral)", (int)info);

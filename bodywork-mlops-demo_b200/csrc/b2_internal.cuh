@@ -57,7 +57,7 @@ struct b2_ctx {
   // tcgen05 path scratch
   double* tc_part = nullptr;           // [sm_count][kTcAccElems]   per-CTA fp64 partial Gram (col-major)
   double* tc_side = nullptr;           // [sm_count][kTcSideDoubles]
-  double* tc_red = nullptr;            // [kTcAccElems + 8] reduced over CTAs
+  double* tc_red = nullptr;            // [kTcAccElems + 16 + 129 + pad]: reduced partials, y sums, barrier slot, shift
   float* shift = nullptr;              // [64][kMaxD + 1] partial sums of the row sample -> per-column shift c
   bool tc_attr_set = false;
   bool solve_attr_set = false;

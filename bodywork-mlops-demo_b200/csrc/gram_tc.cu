@@ -8,12 +8,16 @@
 //   HBM --TMA (cp.async.bulk.tensor, evict-first)--> smem raw tile [64 rows][D] (+ y, + row mask)
 //     --16 transform warps: v = x - c (per-column shift), bf16 split v = hi + lo
 //     -- 1 "E" warp: extra columns E = [1, y'_hi, y'_lo] (y' = y - c_y), CUDA-core sums of y', y'^2, rows
-//     --> smem operand tile, K-major canonical layout (8 x 16 B core matrices, no swizzle):
-//            rows j = 0..127 hi | 128..143 E | 144..271 lo        (one 16-byte chunk = 8 consecutive rows of X)
-//     --tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128, N=144, K=16, two per K-step:
-//            D1[i][j] += sum_r hi[r][i] * [hi | E][r][j]      TMEM columns 0..143 / 160..303 (double buffered)
-//            D2[i][j] += sum_r lo[r][i] * [hi | E][r][j]      TMEM columns 320..463 (never drained mid-kernel)
+//     --> operands, K-major canonical layout (8 x 16 B core matrices, no swizzle; one 16-byte chunk =
+//         8 consecutive rows of X for one feature):
+//            smem  rows j = 0..127 hi | 128..143 E                      (B = [hi | E], and A = hi)
+//            D = 128:  A = lo goes to TENSOR MEMORY (tcgen05.st, lane = feature, 4 packed columns per 8 rows);
+//            D < 128:  lo is a third smem block (rows 144..271), A = lo read through a descriptor
+//     --tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128, N=144, K=16, two per K-step:
+//            D1[i][j] += sum_r hi[r][i] * [hi | E][r][j]      TMEM columns 0..143 / 144..287 (double buffered)
+//            D2[i][j] += sum_r lo[r][i] * [hi | E][r][j]      TMEM columns 288..431 (never drained mid-kernel)
 //        so D1[:, :128] = hi^T hi, D2[:, :128] = lo^T hi, column 128 = sum v, columns 129/130 = sum v*y'.
+//        (TMEM columns 432..495: the two stages of the A = lo operand.)
 //     --every `drain_rows` rows: epilogue warps tcgen05.ld the D1 buffer just finished and fold it into this
 //        CTA's fp64 partial in global memory while the MMAs continue into the other D1 buffer; D2 holds
 //        only the small zero-mean lo terms, so its fp32 sums are drained once at the end.
@@ -23,8 +27,8 @@
 // the centring in the solve subtracts almost nothing.  hi+lo carries 16 mantissa bits, i.e. products are
 // accurate to ~2^-17 relative (lo*lo is dropped).
 //
-// tc_finalize_kernel reduces the per-CTA partials in a fixed order (deterministic), and its last block undoes
-// the shift in fp64 and adds the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
+// tc_reduce_kernel sums the per-CTA partials in a fixed order (deterministic); tc_fold_kernel undoes the shift
+// in fp64 and adds the result to the context's raw statistic S = [X 1 y]^T [X 1 y].
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -268,7 +272,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
                int64_t n_rows, int d_arg, const float* __restrict__ shift, int chunk_tiles,
-               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg) {
+               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg) {
+#ifdef B2_DEV_KNOBS
+  const uint32_t dbg = dbg_arg;      // ablation switches (tools/build_dev.sh): results are WRONG when non-zero
+#else
+  constexpr uint32_t dbg = 0u;       // product build: the ablation branches compile away
+  (void)dbg_arg;
+#endif
   const int d = DFIX ? DFIX : d_arg;
   constexpr bool kTS = (DFIX == 128);                         // A = lo from TMEM (needs warp%4 == feature quad)
   constexpr uint32_t kLBO = kTS ? kOpLBO_TS : kOpLBO_SS;
@@ -573,11 +583,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// finalize (one launch): every block reduces a slice of the per-CTA partials in CTA order (deterministic)
+// finalize: tc_reduce_kernel sums the per-CTA partials in CTA order (deterministic)
 //   red[col * 128 + i], col in [0, 288):  col < 144: D1 (A = hi), col >= 144: D2 (A = lo), columns of [hi | E]
 //   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
-// and the last block to finish (atomic ticket) undoes the shift in fp64 and adds the result into the raw
-// statistic S ((d+2)^2, row stride d+2).
+// tc_fold_kernel undoes the shift in fp64 and adds the result into the raw statistic S ((d+2)^2, stride d+2).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, const double* __restrict__ c,
                                                 int d, int idx, double* __restrict__ S) {
@@ -616,11 +625,17 @@ __device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, 
 }
 
 constexpr int kFinalizeThreads = 256;
+constexpr int kRedShiftOff = kTcAccElems + 16;   // red[kRedShiftOff + j]: the shift c_j as fp64 (j = kMaxD: c_y)
 
+// finalize 1: reduce the per-CTA partials (one extra block materialises the shift vector for finalize 2)
 __global__ void __launch_bounds__(kFinalizeThreads)
-tc_finalize_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
-                   double* __restrict__ red, const float* __restrict__ shift, int64_t n_rows, int d,
-                   double* __restrict__ S, unsigned int* __restrict__ ticket) {
+tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
+                 double* __restrict__ red, const float* __restrict__ shift, int64_t n_rows, int d) {
+  if (blockIdx.x == gridDim.x - 1) {
+    for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
+      red[kRedShiftOff + j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
+    return;
+  }
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < kTcAccElems) {
     double s0 = 0.0, s1 = 0.0;                       // two chains: the loads are the latency
@@ -637,24 +652,13 @@ tc_finalize_kernel(const double* __restrict__ part, const double* __restrict__ s
     for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k];
     red[idx] = s;
   }
-  // ---- last block folds ----------------------------------------------------------------------
-  __shared__ bool is_last;
-  __shared__ double c_s[kMaxD + 1];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-    if (is_last) *ticket = 0u;                        // re-arm for the next launch
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
-    c_s[j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
-  __syncthreads();
-  const int dp = d + 2;
-  for (int e = threadIdx.x; e < dp * dp; e += blockDim.x) tc_fold_element(red, c_s, d, e, S);
+}
+
+// finalize 2: one thread per element of S
+__global__ void __launch_bounds__(kFinalizeThreads)
+tc_fold_kernel(const double* __restrict__ red, int d, double* __restrict__ S) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (d + 2) * (d + 2)) tc_fold_element(red, red + kRedShiftOff, d, idx, S);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -798,14 +802,22 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
                                                                           d, ldx, ctx->shift);
   B2_CUDA(cudaGetLastError());
 
+#ifdef B2_DEV_KNOBS
   static const uint32_t wait_ns = []() {   // development knob: suspend-time hint of the pipeline waits
     const char* e = getenv("B2_WAIT_HINT_NS");
     return e ? (uint32_t)atoi(e) : 20000u;
   }();
-  static const uint32_t dbg = []() {       // development knob: bit0 skip MMA2, bit1 skip all MMAs, bit2 skip STS, bit3 skip LDS
+#else
+  constexpr uint32_t wait_ns = 20000u;     // try_wait suspend hint (ns); measured insensitive 0..20000 (r01)
+#endif
+#ifdef B2_DEV_KNOBS
+  static const uint32_t dbg = []() {       // ablations: bit0 skip MMA2, bit1 skip all MMAs, bit2 skip STS, bit3 skip LDS, bit5 skip proxy fence
     const char* e = getenv("B2_TC_DEBUG");
     return e ? (uint32_t)atoi(e) : 0u;
   }();
+#else
+  constexpr uint32_t dbg = 0u;
+#endif
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
 #define B2_LAUNCH_TC(T, DF)                                                                              \
@@ -823,12 +835,15 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   ctx->k_pairs += 1;
 
   const int red_elems = kTcAccElems + 3;
-  tc_finalize_kernel<<<(red_elems + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
-      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n, d, ctx->S,
-      reinterpret_cast<unsigned int*>(ctx->tc_red + kTcAccElems + 12));
+  tc_reduce_kernel<<<(red_elems + kFinalizeThreads - 1) / kFinalizeThreads + 1, kFinalizeThreads, 0, ctx->stream>>>(
+      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n, d);
   B2_CUDA(cudaGetLastError());
-  ctx->launches += 3;
-  ctx->k_launches += 3;
+  const int dp = d + 2;
+  tc_fold_kernel<<<(dp * dp + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
+      ctx->tc_red, d, ctx->S);
+  B2_CUDA(cudaGetLastError());
+  ctx->launches += 4;
+  ctx->k_launches += 4;
   return B2_OK;
 }
 

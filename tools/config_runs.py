@@ -1,0 +1,135 @@
+"""Measure the BASELINE.json configs that are not bench.py's headline line (development / evidence tool).
+
+    python tools/config_runs.py [c3] [c4] [c5] [shapes]  -> gpurun_out/r01_configs.json (one record per config)
+
+  c3      configs[2] on ONE GPU: 100 M x 128 fp32 resident in HBM (51.6 GB) -- the north-star target point
+  c4      configs[3]: D = 32 rows streamed from pinned host DRAM through the C-ABI (B2_MEM_HOST); 200 M rows
+          (26 GB pinned) stand in for 1 B (132 GB): the path is PCIe-bound, the rate does not depend on N
+  c5      configs[4]: 30-day concept-drift replay, D = 1 reference-faithful tranches and a 1 M x 128 variant
+  shapes  device-resident Gram-kernel rate for D in {8, 32, 64, 128} x {f32, bf16}
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bodywork_mlops_demo_b200 as b2  # noqa: E402
+
+PEAK = 6575.1
+out = {}
+
+
+def gram_rate(ctx, X, y, n, d, kind, reps=6):
+    ctx.set_kernel(b2.KERNEL_TCGEN05)
+    best_k, best_t = 1e9, 1e9
+    for _ in range(reps):
+        ctx.gram_reset(d)
+        ctx.timer_start()
+        ctx.gram_accumulate(X, y)
+        coef, b0 = ctx.solve()
+        t = ctx.timer_stop()
+        k, _n = ctx.last_kernel_ms()
+        best_k, best_t = min(best_k, k), min(best_t, t)
+    bpr = d * (4 if kind == "f32" else 2) + 4
+    return {"n": n, "d": d, "x": kind, "gram_kernel_ms": best_k, "fit_ms": best_t,
+            "gram_rows_per_s": n / best_k * 1e3, "fit_rows_per_s": n / best_t * 1e3,
+            "hbm_gbs": n * bpr / best_k / 1e6, "frac_of_measured_peak": n * bpr / best_k / 1e6 / PEAK,
+            "coef_head": [float(c) for c in coef[:2]], "intercept": float(b0)}
+
+
+def c3(ctx):
+    n, d = 100_000_000, 128
+    X, y = ctx.synth(n, d, seed=1234)
+    ctx.sync()
+    r = gram_rate(ctx, X, y, n, d, "f32", reps=5)
+    X.free(); y.free()
+    out["config3_100Mx128_f32_1gpu"] = r
+    print("c3", r, flush=True)
+
+
+def c4(ctx):
+    n, d = 200_000_000, 32
+    Xp, yp = ctx.pinned((n, d), np.float32), ctx.pinned((n,), np.float32)
+    blk = 25_000_000
+    for lo in range(0, n, blk):             # fill the pinned rows from the device generator
+        Xd, yd = ctx.synth(blk, d, seed=77, row_offset=lo)
+        b2.native._check(b2.native.load().b2_copy_d2h(ctx._h, Xp.ptr + lo * d * 4, Xd.ptr, Xd.nbytes), "d2h")
+        b2.native._check(b2.native.load().b2_copy_d2h(ctx._h, yp.ptr + lo * 4, yd.ptr, yd.nbytes), "d2h")
+        Xd.free(); yd.free()
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    est = b2.B200LinearRegression(ctx=ctx)
+    est.fit(Xp.array[:1_000_000], yp.array[:1_000_000], with_spectrum=False)     # warm-up: staging ring
+    best = 1e9
+    for _ in range(2):
+        t0 = time.perf_counter()
+        est.fit(Xp.array, yp.array, with_spectrum=False)
+        best = min(best, time.perf_counter() - t0)
+    gbs = n * (d * 4 + 4) / best / 1e9
+    r = {"n": n, "d": d, "x": "f32 in pinned host memory", "seconds": best, "rows_per_s": n / best,
+         "h2d_gb_per_s": gbs, "note": "PCIe Gen5 x16 bound; 200 M rows stand in for configs[3]'s 1 B (132 GB)",
+         "coef_head": [float(c) for c in est.coef_[:2]]}
+    Xp.free(); yp.free()
+    out["config4_host_streamed_d32"] = r
+    print("c4", r, flush=True)
+
+
+def c5(ctx):
+    from bodywork_mlops_demo_b200 import incremental
+    from oracle import ols_oracle as orc     # data generator only (reference DGP, seeded)
+    res = {}
+    for tag, n, d, days in (("reference_tranches_1440x1", 1440, 1, 30), ("scaled_1Mx128", 1_000_000, 128, 10)):
+        tranches = []
+        for day in range(days):
+            if d == 1:
+                tranches.append(orc.generate_dataset(n, 1, seed=900 + day, alpha=orc.alpha_of_day(1 + day),
+                                                     drop_negative=True, dtype=np.float32))
+            else:
+                Xd, yd = ctx.synth(n, d, seed=900 + day, alpha=orc.alpha_of_day(1 + day))
+                tranches.append((Xd.to_host(), yd.to_host()))
+                Xd.free(); yd.free()
+        incremental.replay(tranches[:2], d, ctx=ctx)                      # warm-up
+        days_res = incremental.replay(tranches, d, mode="incremental", ctx=ctx)
+        secs = [r.seconds for r in days_res[1:]]
+        res[tag] = {"days": days, "rows_per_day": n, "d": d, "median_day_seconds": float(np.median(secs)),
+                    "rows_per_s_per_day": n / float(np.median(secs)),
+                    "last_day_test_r2": days_res[-1].test_r2, "last_day_test_mape": days_res[-1].test_mape,
+                    "coef_head_last": [float(c) for c in days_res[-1].coef[:2]],
+                    "note": "day = score tranche t with model(t-1) + fold tranche t into S + re-solve; host rows "
+                            "(H2D included)"}
+    out["config5_replay"] = res
+    print("c5", res, flush=True)
+
+
+def shapes(ctx):
+    res = []
+    for d in (8, 32, 64, 128):
+        for kind in ("f32", "bf16"):
+            if kind == "bf16" and d % 8:
+                continue
+            n = 40_000_000 if d <= 32 else 10_000_000
+            X, y = ctx.synth(n, d, seed=5, kind=kind)
+            ctx.sync()
+            r = gram_rate(ctx, X, y, n, d, kind)
+            res.append(r)
+            print("shape", r, flush=True)
+            X.free(); y.free()
+    out["gram_kernel_shapes"] = res
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4", "c5", "shapes"]
+    ctx = b2.Context(0)
+    for w in which:
+        {"c3": c3, "c4": c4, "c5": c5, "shapes": shapes}[w](ctx)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
+    prev = json.load(open(path)) if os.path.exists(path) else {}
+    prev.update(out)
+    json.dump(prev, open(path, "w"), indent=1)
+    print("wrote", path)
