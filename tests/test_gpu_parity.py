@@ -453,3 +453,84 @@ def test_service_test_matches_stage_4_metric_definitions(ctx, n, d):
     assert rec["max_residual"].iloc[0] == pytest.approx(want["max_residual"], rel=1e-4)
     assert rec["mean_response_time"].iloc[0] < 8.22e-3      # the reference's recorded 8.22 ms per row over HTTP
     np.testing.assert_allclose(s2.score_batch(model, Xt, ctx), model.predict(Xt.astype(np.float64)), rtol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw C-ABI: strided rows (ldx > d), unaligned buffers, argument errors
+# ------------------------------------------------------------------------------------------------
+def _raw_accumulate(ctx, Xdev_ptr, ydev_ptr, n, d, ldx, x_dtype=0, mask_ptr=None, keep=1):
+    lib = b2.native.load()
+    return lib.b2_gram_accumulate(ctx._h, Xdev_ptr, x_dtype, ydev_ptr, n, d, ldx, b2.native.MEM_DEVICE, mask_ptr, keep)
+
+
+@pytest.mark.parametrize("kernel", [b2.KERNEL_TCGEN05, b2.KERNEL_SIMT])
+def test_strided_rows_ldx_greater_than_d(ctx, kernel):
+    """X given as the first 64 columns of a wider row-major matrix (ldx = 96): TMA global stride / SIMT pitch."""
+    n, d, ldx = 50_001, 64, 96
+    wide, y = orc.generate_dataset(n, ldx, seed=12, dtype=np.float32)
+    Xd, yd = ctx.to_device(wide), ctx.to_device(y)
+    ctx.set_kernel(kernel)
+    ctx.gram_reset(d)
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, n, d, ldx) == 0, b2.native.last_error()
+    S = ctx.gram_export()
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    assert _rel(S, orc.gram_stats(wide[:, :d], y)) < (2e-6 if kernel == b2.KERNEL_TCGEN05 else 1e-12)
+    # scoring with the same pitch
+    lib = b2.native.load()
+    coef = np.linspace(0.1, 0.9, d)
+    stats = np.zeros(10)
+    yhat = ctx.empty((n,), "f32")
+    rc = lib.b2_score(ctx._h, Xd.ptr, 0, n, d, ldx, b2.native.MEM_DEVICE, coef.ctypes.data, 2.0, yd.ptr, None, 1,
+                      yhat.ptr, stats.ctypes.data)
+    assert rc == 0, b2.native.last_error()
+    p = orc.predict(wide[:, :d], coef, 2.0)
+    assert np.max(np.abs(yhat.to_host() - p)) <= np.max(np.abs(p)) * 1e-6
+    np.testing.assert_allclose(stats, orc.score_stats(y, p), rtol=1e-10)
+
+
+def test_unaligned_buffers_fall_back_to_the_simt_kernel(ctx):
+    """AUTO picks the CUDA-core kernel when X / y are not 16-byte aligned; forcing tcgen05 is refused."""
+    n, d = 10_000, 8
+    X, y = orc.generate_dataset(n + 1, d, seed=13, dtype=np.float32)
+    Xd, yd = ctx.to_device(X), ctx.to_device(y)
+    xp, yp = Xd.ptr + d * 4, yd.ptr + 4          # skip one row: y is now 4-byte aligned only
+    ctx.gram_reset(d)
+    assert _raw_accumulate(ctx, xp, yp, n, d, d) == 0, b2.native.last_error()
+    assert _rel(ctx.gram_export(), orc.gram_stats(X[1:], y[1:])) < 1e-12
+    ctx.set_kernel(b2.KERNEL_TCGEN05)
+    ctx.gram_reset(d)
+    assert _raw_accumulate(ctx, xp, yp, n, d, d) == -6      # B2_E_UNSUPPORTED
+    assert "tcgen05 path needs" in b2.native.last_error()
+    ctx.set_kernel(b2.KERNEL_AUTO)
+
+
+def test_argument_errors_return_codes_not_crashes(ctx):
+    lib = b2.native.load()
+    X, y = orc.generate_dataset(100, 4, seed=1, dtype=np.float32)
+    Xd, yd = ctx.to_device(X), ctx.to_device(y)
+    ctx.gram_reset(4)
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, 100, 5, 5) == -1          # d differs from the statistic's d
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, 100, 4, 3) == -1          # ldx < d
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, -1, 4, 4) == -1
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, 100, 4, 4, x_dtype=7) == -1
+    assert _raw_accumulate(ctx, None, yd.ptr, 100, 4, 4) == -1            # null X
+    assert lib.b2_gram_reset(ctx._h, 129) == -1 and lib.b2_gram_reset(ctx._h, 0) == -1
+    assert lib.b2_ctx_set_drain_rows(ctx._h, 100) == -1                   # not a multiple of the 64-row tile
+    with pytest.raises(RuntimeError, match="alpha must be >= 0"):
+        ctx.gram_reset(4); ctx.gram_accumulate(Xd, yd); ctx.solve(alpha=-1.0)
+    assert _raw_accumulate(ctx, Xd.ptr, yd.ptr, 0, 4, 4) == 0             # empty block is a no-op
+    ctx.gram_reset(4)
+    ctx.gram_accumulate(Xd, yd)
+    assert ctx.gram_export()[4, 4] == 100
+
+
+def test_masked_tail_tile_on_the_tensor_core_path(ctx):
+    """n not a multiple of the 64-row tile AND a row mask: TMA zero-fill + mask bytes + the E warp's row validity."""
+    n, d = 64 * 500 + 37, 128
+    X, y = orc.generate_dataset(n, d, seed=14, dtype=np.float32)
+    mask = (np.random.RandomState(2).rand(n) < 0.7).astype(np.uint8)
+    S = _gram(ctx, X, y, b2.KERNEL_TCGEN05, mask=mask, keep=1)
+    assert S[d, d] == int(mask.sum())
+    assert _rel(S, orc.gram_stats(X[mask == 1], y[mask == 1])) < 2e-6
+    S0 = _gram(ctx, X, y, b2.KERNEL_TCGEN05, mask=mask, keep=0)
+    assert S0[d, d] == n - int(mask.sum())
