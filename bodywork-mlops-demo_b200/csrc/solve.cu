@@ -112,7 +112,7 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
         double a[kNB];
         const int row = kb + (lane & (kNB - 1));
 #pragma unroll
-        for (int c = 0; c < kNB; ++c) a[c] = A[row * pitch + kb + c];   // full row; only c <= lane is meaningful
+        for (int c = 0; c < kNB; ++c) a[c] = lane < kNB ? A[row * pitch + kb + c] : 0.0;   // only c <= lane is meaningful
         double my_inv = 1.0;
         int first_bad = 0;
 #pragma unroll
@@ -127,6 +127,7 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
 #pragma unroll
           for (int c = k + 1; c < kNB; ++c) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);
         }
+        __syncwarp();
         if (lane < kNB) {
 #pragma unroll
           for (int c = 0; c < kNB; ++c) if (c <= lane) A[row * pitch + kb + c] = a[c];
@@ -233,14 +234,15 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
           const int col = lane & (kNB - 1);
           double lt[kNB];                                // lt[k] = L[kb+k][kb+col]
 #pragma unroll
-          for (int k = 0; k < kNB; ++k) lt[k] = A[(kb + k) * pitch + kb + col];
-          double z = r[kb + col];
-          const double dinv = invd[kb + col];
+          for (int k = 0; k < kNB; ++k) lt[k] = lane < kNB ? A[(kb + k) * pitch + kb + col] : 0.0;
+          double z = lane < kNB ? r[kb + col] : 0.0;
+          const double dinv = lane < kNB ? invd[kb + col] : 0.0;
 #pragma unroll
           for (int k = kNB - 1; k >= 0; --k) {
             const double bk = __shfl_sync(0xffffffffu, z * dinv, k);
             z = (lane == k) ? bk : ((lane < k) ? fma(-lt[k], bk, z) : z);   // lanes > k are already final
           }
+          __syncwarp();
           if (lane < kNB) r[kb + lane] = z;
         } else {
           for (int k = nb - 1; k >= 0; --k) {
