@@ -17,6 +17,7 @@ from . import build as _build
 F32, BF16 = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
+PRECISION_SPLIT, PRECISION_BF16 = 0, 1
 E_SINGULAR = -4
 MAX_D = 128
 
@@ -34,6 +35,7 @@ _SIGNATURES = {
     "b2_ctx_info": (C.c_int, [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "b2_ctx_set_kernel": (C.c_int, [_vp, C.c_int]),
     "b2_ctx_set_drain_rows": (C.c_int, [_vp, C.c_int]),
+    "b2_ctx_set_precision": (C.c_int, [_vp, C.c_int]),
     "b2_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "b2_dev_free": (C.c_int, [_vp, _vp]),
     "b2_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -242,6 +244,10 @@ class Context:
 
     def set_kernel(self, kernel: int) -> None:
         _check(load().b2_ctx_set_kernel(self._h, int(kernel)), "b2_ctx_set_kernel")
+
+    def set_precision(self, precision: int) -> None:
+        """PRECISION_SPLIT (default, bf16 hi+lo operands) or PRECISION_BF16 (single bf16 operand, 'bf16-accum')."""
+        _check(load().b2_ctx_set_precision(self._h, int(precision)), "b2_ctx_set_precision")
 
     def set_drain_rows(self, rows: int) -> None:
         _check(load().b2_ctx_set_drain_rows(self._h, int(rows)), "b2_ctx_set_drain_rows")

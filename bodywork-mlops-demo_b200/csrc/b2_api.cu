@@ -258,6 +258,15 @@ int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows) {
   return B2_OK;
 }
 
+int b2_ctx_set_precision(b2_ctx* ctx, int precision) {
+  if (ctx == nullptr || (precision != B2_PRECISION_SPLIT && precision != B2_PRECISION_BF16)) {
+    set_error("precision must be B2_PRECISION_SPLIT or B2_PRECISION_BF16");
+    return B2_E_ARG;
+  }
+  ctx->precision = precision;
+  return B2_OK;
+}
+
 // ---- buffers ------------------------------------------------------------------------------------
 int b2_dev_alloc(b2_ctx* ctx, size_t bytes, void** out) {
   if (int r = use_device(ctx)) return r;

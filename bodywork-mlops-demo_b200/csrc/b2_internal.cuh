@@ -50,6 +50,7 @@ struct b2_ctx {
 
   int kernel_mode = B2_KERNEL_AUTO;
   int drain_rows = 8192;
+  int precision = B2_PRECISION_SPLIT;
 
   int d = 0;                           // feature count of the current statistic (0 = not reset)
   double* S = nullptr;                 // device, kMaxS*kMaxS (only (d+2)^2 used, row stride d+2)

@@ -267,7 +267,10 @@ __global__ void tc_shift_kernel(const T* __restrict__ X, const float* __restrict
 // ------------------------------------------------------------------------------------------
 // DFIX = 128: feature count known at compile time (immediate smem offsets, no index arithmetic in
 // the transform loop); DFIX = 0: runtime d (any multiple of 4 / 8 up to 128).
-template <typename T, int DFIX>
+// SPLIT = true : operands hi + lo (16 mantissa bits, the default);
+// SPLIT = false: single bf16 operand hi = rn(x - c) ("bf16-accum" mode of BASELINE.json configs[1]): half the MMAs,
+//                no lo arithmetic; the operand rounding error (2^-9 relative, zero mean) averages out as 1/sqrt(n).
+template <typename T, int DFIX, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
@@ -380,7 +383,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
           const uint64_t b_desc = make_smem_desc(op_addr + k2 * 2 * kLBO, kLBO);            // [hi | E], also A = hi
           if (!(dbg & 2u)) umma_bf16(tmem_d1, b_desc, b_desc, (in_chunk > 0 || k2 > 0) ? 1u : 0u);
-          if (!(dbg & 3u)) {
+          if (SPLIT && !(dbg & 3u)) {
             if constexpr (kTS) {
               umma_bf16_ts(tmem_base + kTmemD2Col, tmem_base + kTmemALoCol + (uint32_t)(os * 32 + k2 * 8), b_desc,
                            (it > 0 || k2 > 0) ? 1u : 0u);
@@ -483,8 +486,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll 1
     for (int p = 0; p < kTcN / 16; ++p) {
       uint32_t r[16];
-      tmem_ld16(lane_base + kTmemD2Col + (uint32_t)(p * 16), r);
-      tmem_ld_wait();
+      if constexpr (SPLIT) {
+        tmem_ld16(lane_base + kTmemD2Col + (uint32_t)(p * 16), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;     // no lo accumulator in single-operand mode
+      }
       double* dst = my_part + (size_t)(kTcN + p * 16) * kTcM;
 #pragma unroll
       for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(r[j]);
@@ -544,10 +552,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           uint32_t hp[4], lp[4];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
+          for (int p = 0; p < 4; ++p) {
+            if constexpr (SPLIT) {
+              split2(v[2 * p], v[2 * p + 1], hp[p], lp[p]);
+            } else {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * p], v[2 * p + 1]);
+              hp[p] = *reinterpret_cast<const uint32_t*>(&h);
+              lp[p] = 0u;
+            }
+          }
           if (!(dbg & 4u)) {
             st_shared_v4(op_addr + tdst[s], hp);
-            if constexpr (kTS) {
+            if constexpr (!SPLIT) {
+              // single-operand mode: no lo block / TMEM operand
+            } else if constexpr (kTS) {
               // lane l of this warp owns TMEM lane 32*(warp%4)+l == feature i; K group g -> 4 packed columns
               tmem_st4(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemALoCol +
                            (uint32_t)(os * 32 + (tr0[s] >> 3) * 4), lp);
@@ -557,7 +575,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
       }
-      if constexpr (kTS) {
+      if constexpr (kTS && SPLIT) {
         tmem_st_wait();
         tc_fence_before();
       }
@@ -785,12 +803,13 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   if (chunk_tiles < 1) chunk_tiles = 1;
 
   if (!ctx->tc_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmemBytes));
-    B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmemBytes));
+#define B2_SET_SMEM(T, DF, SP) \
+  B2_CUDA(cudaFuncSetAttribute(gram_tc_kernel<T, DF, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes))
+    B2_SET_SMEM(float, 128, true); B2_SET_SMEM(float, 0, true);
+    B2_SET_SMEM(float, 128, false); B2_SET_SMEM(float, 0, false);
+    B2_SET_SMEM(__nv_bfloat16, 128, true); B2_SET_SMEM(__nv_bfloat16, 0, true);
+    B2_SET_SMEM(__nv_bfloat16, 128, false); B2_SET_SMEM(__nv_bfloat16, 0, false);
+#undef B2_SET_SMEM
     ctx->tc_attr_set = true;
   }
 
@@ -820,15 +839,19 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 #endif
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
-#define B2_LAUNCH_TC(T, DF)                                                                              \
-  gram_tc_kernel<T, DF><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                    \
+#define B2_LAUNCH_TC(T, DF, SP)                                                                          \
+  gram_tc_kernel<T, DF, SP><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                \
       tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part, \
       ctx->tc_side, wait_ns, dbg)
+#define B2_LAUNCH_TC_D(T, SP) \
+  do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)
+  const bool split = ctx->precision == B2_PRECISION_SPLIT;
   if (x_dtype == B2_F32) {
-    if (d == 128) B2_LAUNCH_TC(float, 128); else B2_LAUNCH_TC(float, 0);
+    if (split) B2_LAUNCH_TC_D(float, true); else B2_LAUNCH_TC_D(float, false);
   } else {
-    if (d == 128) B2_LAUNCH_TC(__nv_bfloat16, 128); else B2_LAUNCH_TC(__nv_bfloat16, 0);
+    if (split) B2_LAUNCH_TC_D(__nv_bfloat16, true); else B2_LAUNCH_TC_D(__nv_bfloat16, false);
   }
+#undef B2_LAUNCH_TC_D
 #undef B2_LAUNCH_TC
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][1], ctx->stream));

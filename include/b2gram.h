@@ -46,6 +46,10 @@ extern "C" {
 #define B2_KERNEL_SIMT 1   /* fp64-accumulating CUDA-core kernel (any D <= 128)       */
 #define B2_KERNEL_TCGEN05 2 /* TMA -> smem -> bf16 hi/lo split -> tcgen05.mma -> TMEM   */
 
+/* operand precision of the tcgen05 Gram kernel (b2_ctx_set_precision) */
+#define B2_PRECISION_SPLIT 0 /* bf16 hi + lo operands (16 mantissa bits), default: coef error ~2e-6 at any n */
+#define B2_PRECISION_BF16 1  /* single bf16 operand ("bf16-accum", BASELINE.json configs[1]): error ~2.4e-2/sqrt(n) */
+
 /* error codes */
 #define B2_OK 0
 #define B2_E_ARG (-1)
@@ -70,6 +74,8 @@ int b2_ctx_info(b2_ctx* ctx, char* name, int name_cap, int* sm_count, size_t* hb
 int b2_ctx_set_kernel(b2_ctx* ctx, int kernel);
 /* rows of fp32 tensor-core accumulation before a TMEM drain into fp64 (default 8192) */
 int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows);
+/* B2_PRECISION_*: operand precision of the tensor-core path (the CUDA-core kernel is always exact) */
+int b2_ctx_set_precision(b2_ctx* ctx, int precision);
 
 /* ---- caller-owned buffers (helpers; the Python shim has no other CUDA binding) ------------ */
 int b2_dev_alloc(b2_ctx* ctx, size_t bytes, void** out);

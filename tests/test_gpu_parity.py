@@ -534,3 +534,29 @@ def test_masked_tail_tile_on_the_tensor_core_path(ctx):
     assert _rel(S, orc.gram_stats(X[mask == 1], y[mask == 1])) < 2e-6
     S0 = _gram(ctx, X, y, b2.KERNEL_TCGEN05, mask=mask, keep=0)
     assert S0[d, d] == n - int(mask.sum())
+
+
+@pytest.mark.parametrize("kind", ["f32", "bf16"])
+def test_single_bf16_operand_mode_meets_the_contract_at_large_n(ctx, kind):
+    """B2_PRECISION_BF16 ('bf16-accum', BASELINE.json configs[1]): one bf16 operand, fp32 accumulate.  The operand
+    rounding error is zero-mean, so the coefficient error falls as 1/sqrt(n): asserted < 1e-4 (the contract) at
+    n = 2 M and compared with the default split mode on the same rows."""
+    n, d = 2_000_000, 128
+    X, y = ctx.synth(n, d, seed=21, kind=kind)
+    Xh, yh = X.to_host(), y.to_host()
+    Xf = (Xh if kind == "f32" else b2.native.from_bf16_bits(Xh)).astype(np.float64)
+    fo = orc.fit_from_stats(orc.gram_stats(Xf, yh.astype(np.float64)))
+    errs = {}
+    for mode in (b2.PRECISION_SPLIT, b2.PRECISION_BF16):
+        ctx.set_precision(mode)
+        ctx.set_kernel(b2.KERNEL_TCGEN05)
+        try:
+            ctx.gram_reset(d); ctx.gram_accumulate(X, y)
+            coef, _ = ctx.solve()
+            assert ctx.gram_export()[d, d] == n
+        finally:
+            ctx.set_precision(b2.PRECISION_SPLIT); ctx.set_kernel(b2.KERNEL_AUTO)
+        errs[mode] = float(np.max(np.abs(coef - fo["coef"])))
+    assert errs[b2.PRECISION_SPLIT] < COEF_TOL
+    assert errs[b2.PRECISION_BF16] < 1e-4
+    X.free(); y.free()

@@ -8,6 +8,8 @@ kind = sys.argv[3] if len(sys.argv) > 3 else "f32"
 ctx = b2.Context(0)
 X, y = ctx.synth(n, d, kind=kind)
 ctx.set_kernel(b2.KERNEL_TCGEN05)
+if os.environ.get("B2_PRECISION") == "bf16":
+    ctx.set_precision(b2.PRECISION_BF16)
 best = 1e9
 for _ in range(8):
     ctx.gram_reset(d); ctx.gram_accumulate(X, y); ctx.sync()
