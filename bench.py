@@ -211,6 +211,9 @@ def main() -> None:
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--precision", default="split", choices=["split", "bf16"],
+                    help="tensor-core operand precision: bf16 hi+lo split (default) or a single bf16 operand")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -245,6 +248,7 @@ def main() -> None:
     kind = args.x_dtype
     X, y = ctx.synth(rows, D, seed=1234, row_offset=rank * rows, kind=kind)
     ctx.set_kernel(b2.KERNEL_TCGEN05)
+    ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
     ctx.sync()
 
     def step():
@@ -323,6 +327,32 @@ def main() -> None:
                "coef_linf_vs_resident": float(np.max(np.abs(est.coef_ - coef)))}
         Xp.free(); yp.free()
 
+    # ---- other operand / storage variants of configs[1] (N = 1 only; kernel + whole-fit rates, same timing rules) --
+    variants = None
+    if world == 1 and not args.no_variants:
+        variants = {}
+        for vk, vprec in ((kind, "bf16"), ("bf16" if kind == "f32" else "f32", "split"),
+                          ("bf16" if kind == "f32" else "f32", "bf16")):
+            Xv, yv = (X, y) if vk == kind else ctx.synth(rows, D, seed=1234, kind=vk)
+            ctx.set_kernel(b2.KERNEL_TCGEN05)
+            ctx.set_precision(b2.PRECISION_BF16 if vprec == "bf16" else b2.PRECISION_SPLIT)
+            for _ in range(3):
+                ctx.gram_reset(D); ctx.gram_accumulate(Xv, yv); ctx.solve()
+            ctx.last_kernel_ms()
+            ctx.sync(); ctx.timer_start()
+            for _ in range(10):
+                ctx.gram_reset(D); ctx.gram_accumulate(Xv, yv); cv, _b = ctx.solve()
+            vms = ctx.timer_stop() / 10
+            kms, kl = ctx.last_kernel_ms()
+            bpr = D * (4 if vk == "f32" else 2) + 4
+            variants[f"x_{vk}_operands_{'bf16x1' if vprec == 'bf16' else 'bf16x2'}"] = {
+                "fit_rows_per_s": rows / vms * 1e3, "gram_kernel_ms": kms / max(kl, 1),
+                "frac_of_hbm_peak": rows * bpr / (kms / max(kl, 1)) / 1e6 / peak,
+                "coef_linf_vs_headline_fit": float(np.max(np.abs(cv - coef)))}
+            ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
+            if vk != kind:
+                Xv.free(); yv.free()
+
     # ---- CPU baseline: sklearn on the host cores, bounded sample, rank 0 at N = 1 only --------------------
     cpu = None
     parity = None
@@ -350,10 +380,10 @@ def main() -> None:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16x2 (hi+lo) MMA operands, f32 accumulate, f64 fold+solve",
+            "vs_baseline": None, "dtype": ("bf16x2 (hi+lo)" if args.precision == "split" else "bf16x1") + " MMA operands, f32 accumulate, f64 fold+solve",
             "data": "synthetic (device Philox, reference DGP: X~U(0,100), y=1+0.5*sum(X)+10*eps)",
             "config": workload_config(world, kind), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "variants": variants,
             "host_wall_ms_per_step": 1e3 * t_host / args.steps,
             "coef_head": [float(c) for c in coef[:3]], "intercept": float(b0),
         }
