@@ -20,11 +20,23 @@ constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr double kEpsF64 = 2.220446049250313e-16;
 
 constexpr int kNStats = 10;   // include/b2gram.h: b2_score stats_out layout
+// 1/x for x >= eps_f64 without the library's slow-path call: fp32 seed, two Newton steps in fp64
+__device__ __forceinline__ double rcp_pos(double x) {
+  double r = (double)__frcp_rn((float)x);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 struct RowStats {
   double ape = 0.0, sse = 0.0, sy = 0.0, syy = 0.0, mx = 0.0, cnt = 0.0, sp = 0.0, spp = 0.0, syp = 0.0, mxape = 0.0;
   __device__ void add(double y, double p) {
     const double e = fabs(p - y);
-    ape += e / fmax(fabs(y), kEpsF64);            // sklearn MAPE term (stage_1_train_model.py:81)
+    const double ay = fabs(y);
+    // |y| in the float range (the overwhelmingly common case): one cheap reciprocal serves both APE terms
+    const bool common = ay > 1e-30 && ay < 1e30;
+    const double term = common ? e * rcp_pos(ay) : e / fmax(ay, kEpsF64);
+    ape += term;                                  // sklearn MAPE term (stage_1_train_model.py:81)
     sse += (y - p) * (y - p);
     sy += y;
     syy += y * y;
@@ -33,7 +45,7 @@ struct RowStats {
     sp += p;                                      // Pearson correlation terms (stage_4...:103 "r_squared")
     spp += p * p;
     syp += y * p;
-    mxape = fmax(mxape, e / fabs(y));             // |score/label - 1| (stage_4...:89,104); inf when label == 0
+    mxape = fmax(mxape, common ? term : e / ay);  // |score/label - 1| (stage_4...:89,104); inf when label == 0
   }
 };
 __device__ __forceinline__ bool stat_is_max(int k) { return k == 4 || k == 9; }
@@ -143,6 +155,133 @@ score_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const doubl
   }
 }
 
+// ---- fast path (d % 4 == 0, 16-byte aligned rows): 4 rows per warp iteration, 32 warps per SM ---------------
+// Each lane loads 16 B of each of 4 rows (independent 128-bit loads in flight), forms its 4-term partial dot in
+// fp64, and the 4 x 32 partials are reduced with a transposing butterfly (6 double shuffles instead of 20): after
+// it, lane l holds the full dot of row ((l >> 4) & 1) * 2 + ((l >> 3) & 1).  The 4 lanes with (l & 7) == 0 then
+// update the statistics of their own row in parallel.
+template <typename T>
+__device__ __forceinline__ void load_row4(const T* __restrict__ row, int lane, bool pred, float (&x)[4]);
+// Predicated streaming loads as volatile PTX: the compiler keeps the four row loads of an iteration in
+// distinct registers and issues them back to back (with plain __ldg it re-used one register quad and
+// serialised the loads -- ncu r01: every row's first conversion stalled on long_scoreboard).
+template <>
+__device__ __forceinline__ void load_row4<float>(const float* __restrict__ row, int lane, bool pred, float (&x)[4]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@p ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+      : "l"(reinterpret_cast<const float4*>(row) + lane), "r"((int)pred));
+}
+template <>
+__device__ __forceinline__ void load_row4<__nv_bfloat16>(const __nv_bfloat16* __restrict__ row, int lane, bool pred,
+                                                         float (&x)[4]) {
+  uint32_t u0, u1;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t"
+      "@p ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];\n\t}"
+      : "=r"(u0), "=r"(u1)
+      : "l"(reinterpret_cast<const uint2*>(row) + lane), "r"((int)pred));
+  x[0] = __uint_as_float(u0 << 16); x[1] = __uint_as_float(u0 & 0xffff0000u);
+  x[2] = __uint_as_float(u1 << 16); x[3] = __uint_as_float(u1 & 0xffff0000u);
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+constexpr int kRowsPerIter = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kScoreThreads, 4)
+score_kernel_rows8(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const double* __restrict__ coef,
+                   const float* __restrict__ y, const uint8_t* __restrict__ mask, int keep,
+                   float* __restrict__ yhat, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool col_ok = lane * 4 < d;
+  double cf[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cf[k] = (lane * 4 + k < d) ? coef[lane * 4 + k] : 0.0;
+  const double b0 = coef[kMaxD];
+  const int my_row = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);   // row (of 4) this lane owns after the reduce
+  RowStats st;
+  const int64_t warps_total = (int64_t)gridDim.x * kScoreWarps;
+  const int64_t gw = (int64_t)blockIdx.x * kScoreWarps + warp;
+  for (int64_t base = gw * kRowsPerIter; base < n; base += warps_total * kRowsPerIter) {
+    float x[kRowsPerIter][4];
+    unsigned use_bits = 0;
+    float y_mine = 0.f;                           // this lane's row label, fetched together with the X loads
+    if (y != nullptr && (lane & 7) == 0 && base + my_row < n) y_mine = __ldg(y + base + my_row);
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) {     // 4 independent 128-bit loads in flight per lane
+      const int64_t row = base + r;
+      bool use = row < n;
+      if (use && mask != nullptr) use = (__ldg(mask + row) == (uint8_t)keep);
+      use_bits |= (use ? 1u : 0u) << r;
+      load_row4<T>(X + row * ldx, lane, use && col_ok, x[r]);
+    }
+    double p[kRowsPerIter];
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) {
+      double a = (double)x[r][0] * cf[0];
+      a = fma((double)x[r][1], cf[1], a);
+      a = fma((double)x[r][2], cf[2], a);
+      p[r] = fma((double)x[r][3], cf[3], a);
+    }
+    // transposing butterfly: keep the half of the rows selected by the lane bit, add the partner's copy
+    double q2[2], q1;
+    {
+      const bool hi = (lane & 16) != 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const double send = hi ? p[r] : p[r + 2];
+        const double keepv = hi ? p[r + 2] : p[r];
+        q2[r] = keepv + shfl_xor_d(send, 16);
+      }
+    }
+    {
+      const bool hi = (lane & 8) != 0;
+      const double send = hi ? q2[0] : q2[1];
+      const double keepv = hi ? q2[1] : q2[0];
+      q1 = keepv + shfl_xor_d(send, 8);
+    }
+    q1 += shfl_xor_d(q1, 4);
+    q1 += shfl_xor_d(q1, 2);
+    q1 += shfl_xor_d(q1, 1);
+    if ((lane & 7) == 0) {
+      const int64_t row = base + my_row;
+      if (row < n) {
+        const bool use = (use_bits >> my_row) & 1u;
+        const double pr = q1 + b0;
+        if (yhat != nullptr) yhat[row] = use ? (float)pr : 0.f;
+        if (use && y != nullptr) st.add((double)y_mine, pr);
+      }
+    }
+  }
+  // block reduce: first across the 4 row-owning lanes of each warp (lanes 0, 8, 16, 24), then across warps
+  double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+#pragma unroll
+  for (int k = 0; k < kNStats; ++k) {
+#pragma unroll
+    for (int o = 16; o >= 8; o >>= 1) {
+      const double other = shfl_xor_d(v[k], o);
+      v[k] = stat_is_max(k) ? fmax(v[k], other) : v[k] + other;
+    }
+  }
+  __shared__ double red[kScoreWarps][kNStats];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNStats; ++k) red[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNStats) {
+    const int k = threadIdx.x;
+    double acc = 0.0;
+    for (int w = 0; w < kScoreWarps; ++w) acc = stat_is_max(k) ? fmax(acc, red[w][k]) : acc + red[w][k];
+    part[(size_t)blockIdx.x * kNStats + k] = acc;
+  }
+}
+
 // acc[0..5] (at part + n_ctas*6 ... see launch) = combine over CTAs in order; `first` overwrites.
 __global__ void score_reduce_kernel(const double* __restrict__ part, int n_ctas, int first, double* __restrict__ acc) {
   const int k = threadIdx.x;
@@ -164,7 +303,15 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
   if (want < 1) want = 1;
   const int grid = (int)(want < ctx->score_ctas ? want : ctx->score_ctas);
   double* acc = ctx->score_part + (size_t)ctx->score_ctas * kNStats;
-  if (x_dtype == B2_F32)
+  const bool rows16 = vec && ((ldx * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0 || x_dtype != B2_F32);
+  if (rows16 && x_dtype == B2_F32)
+    score_kernel_rows8<float><<<grid, kScoreThreads, 0, ctx->stream>>>(static_cast<const float*>(X), n, d, ldx,
+                                                                       ctx->coef_dev, y, mask, keep, yhat,
+                                                                       ctx->score_part);
+  else if (rows16)
+    score_kernel_rows8<__nv_bfloat16><<<grid, kScoreThreads, 0, ctx->stream>>>(
+        static_cast<const __nv_bfloat16*>(X), n, d, ldx, ctx->coef_dev, y, mask, keep, yhat, ctx->score_part);
+  else if (x_dtype == B2_F32)
     score_kernel<float><<<grid, kScoreThreads, 0, ctx->stream>>>(static_cast<const float*>(X), n, d, ldx,
                                                                  ctx->coef_dev, y, mask, keep, yhat, vec,
                                                                  ctx->score_part);
