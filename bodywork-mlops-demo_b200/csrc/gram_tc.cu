@@ -57,8 +57,11 @@ constexpr uint32_t kTmemALoCol = 432;                         // TS: A = lo oper
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;     // 131072
 constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;         // 200704
-constexpr uint32_t kOffMask = kOffY + kRawStages * 256;
-constexpr uint32_t kOffBar = kOffMask + kRawStages * 128;
+constexpr int kMaxPack = 4;                                             // original rows per 128-wide super-row
+constexpr uint32_t kYStageBytes = kTcRows * kMaxPack * 4;               // 1024
+constexpr uint32_t kMStageBytes = kTcRows * kMaxPack;                   // 256
+constexpr uint32_t kOffMask = kOffY + kRawStages * kYStageBytes;
+constexpr uint32_t kOffBar = kOffMask + kRawStages * kMStageBytes;
 constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 4;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
@@ -274,7 +277,7 @@ template <typename T, int DFIX, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
-               int64_t n_rows, int d_arg, const float* __restrict__ shift, int chunk_tiles,
+               int64_t n_rows, int d_arg, int pack, int64_t n_shift, const float* __restrict__ shift, int chunk_tiles,
                double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg) {
 #ifdef B2_DEV_KNOBS
   const uint32_t dbg = dbg_arg;      // ablation switches (tools/build_dev.sh): results are WRONG when non-zero
@@ -336,8 +339,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // zero the operand stages once: feature rows >= d, the unused E rows and the lo/hi padding read as 0
   for (uint32_t o = threadIdx.x * 16; o < kOpStages * kOpStageBytes; o += kThreads * 16)
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
+  // packed rows (pack > 1): super-row feature i is original feature i % (128 / pack) -> the shift repeats
+  const int d_orig = d / pack;
   for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
-    shift_s[j] = (j < d || j == kMaxD) ? shift_value(shift, j, n_rows) : 0.f;
+    shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift) : (j < d ? shift_value(shift, j % d_orig, n_shift) : 0.f);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -348,7 +353,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(kTcRows * d * sizeof(T)) + kTcRows * 4 + (has_mask ? kTcRows : 0);
+      const uint32_t tx = (uint32_t)(kTcRows * d * sizeof(T)) + kTcRows * pack * 4 + (has_mask ? kTcRows * pack : 0);
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -357,9 +362,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_expect_tx(full, tx);
         const int64_t row0 = (tile_begin + it) * kTcRows;
         tma_load_2d(sbase + kOffRaw + s * kRawStageBytes, &tmX, 0, (int)row0, full);
-        if (y_map_2d) tma_load_2d(sbase + kOffY + s * 256, &tmY, 0, (int)(row0 >> 2), full);
-        else tma_load_1d(sbase + kOffY + s * 256, &tmY, (int)row0, full);
-        if (has_mask) tma_load_1d(sbase + kOffMask + s * 128, &tmM, (int)row0, full);
+        const int sub0 = (int)row0 * pack;                               // first original row of the tile
+        if (y_map_2d) tma_load_2d(sbase + kOffY + s * kYStageBytes, &tmY, 0, sub0 >> 2, full);
+        else tma_load_1d(sbase + kOffY + s * kYStageBytes, &tmY, sub0, full);
+        if (has_mask) tma_load_1d(sbase + kOffMask + s * kMStageBytes, &tmM, sub0, full);
         if (++s == kRawStages) { s = 0; ph ^= 1; }
       }
     }
@@ -411,27 +417,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(bar_op_empty + 8 * os, oph ^ 1, wait_ns);
       tc_fence_after();
       const int64_t row0 = (tile_begin + it) * kTcRows;
-      const uint32_t y_addr = sbase + kOffY + rs * 256;
-      const uint32_t m_addr = sbase + kOffMask + rs * 128;
+      const uint32_t y_addr = sbase + kOffY + rs * kYStageBytes;
+      const uint32_t m_addr = sbase + kOffMask + rs * kMStageBytes;
       const uint32_t e_addr = sbase + kOffOp + os * kOpStageBytes + kOpEOff;
       const int64_t left = n_rows - row0;
       const int rows_valid = left < kTcRows ? (int)left : kTcRows;
       float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
       for (int h = 0; h < kTcRows / 32; ++h) {
-        const int rr = lane + 32 * h;
-        bool use = rr < rows_valid;
-        if (use && has_mask) use = (ld_shared_u8(m_addr + rr) == (uint32_t)keep);
-        const float yv = use ? ld_shared_f32(y_addr + rr * 4) - c_y : 0.f;
-        uint32_t yh, yl;
-        split2(yv, 0.f, yh, yl);
+        const int rr = lane + 32 * h;               // super-row inside the tile
         const uint32_t dst = e_addr + (rr >> 3) * kLBO + (rr & 7) * 2;
-        st_shared_u16(dst, use ? 0x3F80u : 0u);   // bf16(1.0)
-        st_shared_u16(dst + 16, yh);
-        st_shared_u16(dst + 32, yl);
-        a += yv;
-        b = fmaf(yv, yv, b);
-        c += use ? 1.f : 0.f;
+        for (int bl = 0; bl < pack; ++bl) {         // original row rr * pack + bl -> E columns 3*bl .. 3*bl+2
+          const int sub = rr * pack + bl;
+          bool use = rr < rows_valid;
+          if (use && has_mask) use = (ld_shared_u8(m_addr + sub) == (uint32_t)keep);
+          const float yv = use ? ld_shared_f32(y_addr + sub * 4) - c_y : 0.f;
+          uint32_t yh, yl;
+          split2(yv, 0.f, yh, yl);
+          st_shared_u16(dst + (3 * bl) * 16, use ? 0x3F80u : 0u);   // bf16(1.0): row-validity ("ones") column
+          st_shared_u16(dst + (3 * bl + 1) * 16, yh);
+          st_shared_u16(dst + (3 * bl + 2) * 16, yl);
+          a += yv;
+          b = fmaf(yv, yv, b);
+          c += use ? 1.f : 0.f;
+        }
       }
       sy += (double)a; syy += (double)b; cnt += (double)c;
       fence_proxy_async_smem();
@@ -507,7 +516,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     bool tv[2];
     float tc[2];
     uint32_t tsrc[2], tdst[2];
-    int tr0[2];
+    int tr0[2], tblk[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const int tt = t + kXformWarps * s;
@@ -517,6 +526,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tv[s] = valid && (i < d);
       tc[s] = shift_s[tv[s] ? i : 0];
       tr0[s] = g * 8;
+      tblk[s] = (tv[s] ? i : 0) / d_orig;           // which original row of the super-row this feature belongs to
       tsrc[s] = (uint32_t)(g * 8) * pitch + (uint32_t)(tv[s] ? i : 0) * esz;
       tdst[s] = (uint32_t)g * kLBO + (uint32_t)((i >> 3) * kOpSBO + (i & 7) * 16);
     }
@@ -531,7 +541,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int rows_valid = left < kTcRows ? (int)left : kTcRows;
       const bool full_tile = (!has_mask) && (rows_valid == kTcRows);
       const uint32_t raw_addr = sbase + kOffRaw + rs * kRawStageBytes;
-      const uint32_t m_addr = sbase + kOffMask + rs * 128;
+      const uint32_t m_addr = sbase + kOffMask + rs * kMStageBytes;
       const uint32_t op_addr = sbase + kOffOp + os * kOpStageBytes;
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -546,7 +556,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               bool use = (tr0[s] + k) < rows_valid;
-              if (use && has_mask) use = (ld_shared_u8(m_addr + tr0[s] + k) == (uint32_t)keep);
+              if (use && has_mask) use = (ld_shared_u8(m_addr + (tr0[s] + k) * pack + tblk[s]) == (uint32_t)keep);
               if (!use) v[k] = 0.f;
             }
           }
@@ -606,15 +616,29 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 //   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
 // tc_fold_kernel undoes the shift in fp64 and adds the result into the raw statistic S ((d+2)^2, stride d+2).
 // ------------------------------------------------------------------------------------------
+// `pack` original rows share one 128-wide super-row (d * pack == 128 when pack > 1): original feature a of
+// sub-row blk is super-feature blk*d + a, and its E columns are 128 + 3*blk (+0 ones, +1 y'_hi, +2 y'_lo).
+// The true statistic is the sum over blk of the diagonal (blk, blk) blocks.
 __device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, const double* __restrict__ c,
-                                                int d, int idx, double* __restrict__ S) {
+                                                int d, int pack, int idx, double* __restrict__ S) {
   const int dp = d + 2;
   const int a = idx / dp, b = idx % dp;
   // D1[i][j] = red[j*128 + i], D2[i][j] = red[(144 + j)*128 + i]
   auto D1 = [&](int i, int j) { return red[(size_t)j * kTcM + i]; };
   auto D2 = [&](int i, int j) { return red[(size_t)(kTcN + j) * kTcM + i]; };
-  auto s1 = [&](int i) { return D1(i, 128) + D2(i, 128); };                                  // sum (x_i - c_i)
-  auto sxy = [&](int i) { return D1(i, 129) + D1(i, 130) + D2(i, 129) + D2(i, 130); };       // sum (x_i - c_i) y'
+  auto s1 = [&](int i) {                                                     // sum (x_i - c_i)
+    double t = 0.0;
+    for (int blk = 0; blk < pack; ++blk) t += D1(blk * d + i, 128 + 3 * blk) + D2(blk * d + i, 128 + 3 * blk);
+    return t;
+  };
+  auto sxy = [&](int i) {                                                    // sum (x_i - c_i) y'
+    double t = 0.0;
+    for (int blk = 0; blk < pack; ++blk) {
+      const int r = blk * d + i, e = 128 + 3 * blk;
+      t += D1(r, e + 1) + D1(r, e + 2) + D2(r, e + 1) + D2(r, e + 2);
+    }
+    return t;
+  };
   const double sy = red[kTcAccElems + 0];
   const double syy = red[kTcAccElems + 1];
   const double n = red[kTcAccElems + 2];
@@ -623,9 +647,12 @@ __device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, 
   if (a < d && b < d) {
     const double ca = c[a], cb = c[b];
     // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hi.hi + lo.hi + hi.lo   (lo.lo dropped, ~2^-18 relative)
-    const double hh = 0.5 * (D1(a, b) + D1(b, a));
-    const double hl = D2(a, b) + D2(b, a);
-    val = hh + hl + ca * s1(b) + cb * s1(a) + n * ca * cb;
+    double g = 0.0;
+    for (int blk = 0; blk < pack; ++blk) {
+      const int ia = blk * d + a, ib = blk * d + b;
+      g += 0.5 * (D1(ia, ib) + D1(ib, ia)) + D2(ia, ib) + D2(ib, ia);
+    }
+    val = g + ca * s1(b) + cb * s1(a) + n * ca * cb;
   } else if (a < d || b < d) {
     const int i = a < d ? a : b;
     const int o = a < d ? b : a;  // d (ones) or d+1 (y)
@@ -674,9 +701,9 @@ tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ sid
 
 // finalize 2: one thread per element of S
 __global__ void __launch_bounds__(kFinalizeThreads)
-tc_fold_kernel(const double* __restrict__ red, int d, double* __restrict__ S) {
+tc_fold_kernel(const double* __restrict__ red, int d, int pack, double* __restrict__ S) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (d + 2) * (d + 2)) tc_fold_element(red, red + kRedShiftOff, d, idx, S);
+  if (idx < (d + 2) * (d + 2)) tc_fold_element(red, red + kRedShiftOff, d, pack, idx, S);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -709,8 +736,9 @@ bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, in
 }
 
 static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int es, const float* y, int64_t n, int d,
-                       int64_t ldx, const uint8_t* mask, CUtensorMap* tmX_out, CUtensorMap* tmY_out,
-                       CUtensorMap* tmM_out, int* y_map_2d_out) {
+                       int64_t ldx, int64_t n_y, int pack, const uint8_t* mask, CUtensorMap* tmX_out,
+                       CUtensorMap* tmY_out, CUtensorMap* tmM_out, int* y_map_2d_out) {
+  const cuuint32_t y_box = (cuuint32_t)(kTcRows * pack);   // original rows per tile
   CUtensorMap& tmX = *tmX_out; CUtensorMap& tmY = *tmY_out; CUtensorMap& tmM = *tmM_out;
   memset(&tmM, 0, sizeof(tmM));
   {
@@ -730,18 +758,18 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
   }
   int y_map_2d = 0;
   {
-    cuuint64_t dims[1] = {(cuuint64_t)n};
+    cuuint64_t dims[1] = {(cuuint64_t)n_y};
     cuuint64_t strides[1] = {0};
-    cuuint32_t box[1] = {(cuuint32_t)kTcRows};
+    cuuint32_t box[1] = {y_box};
     cuuint32_t estr[1] = {1};
     CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(y), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       // rank-1 maps refused: view y as [ceil(n/4)][4] (16-byte rows) -- the same bytes land in smem
-      cuuint64_t dims2[2] = {4, (cuuint64_t)((n + 3) / 4)};
+      cuuint64_t dims2[2] = {4, (cuuint64_t)((n_y + 3) / 4)};
       cuuint64_t strides2[1] = {16};
-      cuuint32_t box2[2] = {4, (cuuint32_t)(kTcRows / 4)};
+      cuuint32_t box2[2] = {4, y_box / 4};
       cuuint32_t estr2[2] = {1, 1};
       r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(y), dims2, strides2, box2, estr2,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -758,9 +786,9 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
     return B2_E_ARG;
   }
   if (mask != nullptr) {
-    cuuint64_t dims[1] = {(cuuint64_t)n};
+    cuuint64_t dims[1] = {(cuuint64_t)n_y};
     cuuint64_t strides[1] = {0};
-    cuuint32_t box[1] = {(cuuint32_t)kTcRows};
+    cuuint32_t box[1] = {y_box};
     cuuint32_t estr[1] = {1};
     CUresult r = encode(&tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, const_cast<uint8_t*>(mask), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -775,7 +803,7 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
   return B2_OK;
 }
 
-int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
+int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_in, int d_in, int64_t ldx_in,
                    const uint8_t* mask, int keep) {
   PFN_encodeTiled encode = get_encode();
   if (encode == nullptr) {
@@ -783,17 +811,28 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     return B2_E_CUDA;
   }
   const int es = x_dtype == B2_F32 ? 4 : 2;
+  // Row packing: contiguous rows of 32 / 64 features are viewed as [n / pack][128] super-rows and run on the
+  // D = 128 fast path; the diagonal blocks of the 128 x 128 Gram sum to the true statistic (tc_fold_kernel).
+  // The n % pack leftover rows (at most 3) go through the CUDA-core kernel.
+  int pack = 1;
+  if ((d_in == 32 || d_in == 64) && ldx_in == d_in && n_in >= (int64_t)kTcRows * (128 / d_in)) pack = 128 / d_in;
+  const int64_t n_main = n_in - n_in % pack;           // original rows handled here
+  const int64_t n = n_main / pack;                      // super-rows
+  const int d = d_in * pack;
+  const int64_t ldx = ldx_in * pack;
+  const int64_t n_y = n_main;                           // y / mask elements covered by the tensor maps
   CUtensorMap tmX, tmY, tmM;
   int y_map_2d = 0;
   b2_ctx::TmCache& tc = ctx->tm_cache;
-  const bool cached = tc.X == X && tc.y == y && tc.mask == mask && tc.n == n && tc.ldx == ldx && tc.d == d &&
+  const bool cached = tc.X == X && tc.y == y && tc.mask == mask && tc.n == n_in && tc.ldx == ldx_in && tc.d == d_in &&
                       tc.x_dtype == x_dtype;
   if (cached) {
     memcpy(&tmX, tc.tmX, sizeof(tmX)); memcpy(&tmY, tc.tmY, sizeof(tmY)); memcpy(&tmM, tc.tmM, sizeof(tmM));
     y_map_2d = tc.y_map_2d;
   } else {
-    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d, ldx, mask, &tmX, &tmY, &tmM, &y_map_2d)) return r;
-    tc.X = X; tc.y = y; tc.mask = mask; tc.n = n; tc.ldx = ldx; tc.d = d; tc.x_dtype = x_dtype; tc.y_map_2d = y_map_2d;
+    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d, ldx, n_y, pack, mask, &tmX, &tmY, &tmM, &y_map_2d)) return r;
+    tc.X = X; tc.y = y; tc.mask = mask; tc.n = n_in; tc.ldx = ldx_in; tc.d = d_in; tc.x_dtype = x_dtype;
+    tc.y_map_2d = y_map_2d;
     memcpy(tc.tmX, &tmX, sizeof(tmX)); memcpy(tc.tmY, &tmY, sizeof(tmY)); memcpy(tc.tmM, &tmM, sizeof(tmM));
   }
 
@@ -814,11 +853,11 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   }
 
   if (x_dtype == B2_F32)
-    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n, d, ldx,
-                                                                  ctx->shift);
+    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
+                                                                  ldx_in, ctx->shift);
   else
-    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y, n,
-                                                                          d, ldx, ctx->shift);
+    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
+                                                                          n_in, d_in, ldx_in, ctx->shift);
   B2_CUDA(cudaGetLastError());
 
 #ifdef B2_DEV_KNOBS
@@ -841,8 +880,8 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
 #define B2_LAUNCH_TC(T, DF, SP)                                                                          \
   gram_tc_kernel<T, DF, SP><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                \
-      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, ctx->shift, chunk_tiles, ctx->tc_part, \
-      ctx->tc_side, wait_ns, dbg)
+      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, pack, n_in, ctx->shift, chunk_tiles,  \
+      ctx->tc_part, ctx->tc_side, wait_ns, dbg)
 #define B2_LAUNCH_TC_D(T, SP) \
   do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)
   const bool split = ctx->precision == B2_PRECISION_SPLIT;
@@ -859,14 +898,19 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 
   const int red_elems = kTcAccElems + 3;
   tc_reduce_kernel<<<(red_elems + kFinalizeThreads - 1) / kFinalizeThreads + 1, kFinalizeThreads, 0, ctx->stream>>>(
-      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n, d);
+      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n_in, d_in);
   B2_CUDA(cudaGetLastError());
-  const int dp = d + 2;
+  const int dp = d_in + 2;
   tc_fold_kernel<<<(dp * dp + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
-      ctx->tc_red, d, ctx->S);
+      ctx->tc_red, d_in, pack, ctx->S);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 4;
   ctx->k_launches += 4;
+  if (n_main < n_in) {   // the n % pack leftover rows
+    const char* Xt = static_cast<const char*>(X) + (size_t)n_main * ldx_in * es;
+    return launch_gram_simt(ctx, Xt, x_dtype, y + n_main, n_in - n_main, d_in, ldx_in,
+                            mask != nullptr ? mask + n_main : nullptr, keep);
+  }
   return B2_OK;
 }
 
