@@ -43,8 +43,8 @@ namespace {
 constexpr int kRawStages = 4;
 constexpr int kOpStages = 2;
 constexpr int kXformWarps = 16;
-constexpr int kThreads = 32 * (8 + kXformWarps);  // warps: 0 TMA, 1 MMA(+TMEM alloc), 2 E, 3 idle, 4-7 epilogue, 8.. transform
-constexpr int kProducers = kXformWarps + 1;        // warps that fill an operand stage (transform + E)
+constexpr int kThreads = 32 * (8 + kXformWarps);  // warps: 0 TMA, 1 MMA(+TMEM alloc), 2-3 E, 4-7 epilogue, 8.. transform
+constexpr int kProducers = kXformWarps + 2;        // warps that fill an operand stage (transform + 2 E warps)
 constexpr int kKGroups = kTcRows / 8;              // 8-row K groups per stage
 constexpr uint32_t kRawStageBytes = kTcRows * kMaxD * 4;      // 32768 (fp32, D = 128)
 constexpr uint32_t kOpSBO = 128;                              // bytes between 8-row j groups (core matrices along M/N)
@@ -406,8 +406,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (++os == kOpStages) { os = 0; oph ^= 1; }
       }
     }
-  } else if (warp == 2) {
-    // ===== E warp: extra operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' =====
+  } else if (warp == 2 || warp == 3) {
+    // ===== E warps: extra operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' =====
     const float c_y = shift_s[kMaxD];
     double sy = 0.0, syy = 0.0, cnt = 0.0;
     int rs = 0, os = 0;
@@ -422,10 +422,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const uint32_t e_addr = sbase + kOffOp + os * kOpStageBytes + kOpEOff;
       const int64_t left = n_rows - row0;
       const int rows_valid = left < kTcRows ? (int)left : kTcRows;
+      // warp 2 covers super-rows 0..31 of the tile, warp 3 covers 32..63: one super-row per lane
       float a = 0.f, b = 0.f, c = 0.f;
-#pragma unroll
-      for (int h = 0; h < kTcRows / 32; ++h) {
-        const int rr = lane + 32 * h;               // super-row inside the tile
+      {
+        const int rr = lane + 32 * (warp - 2);      // super-row inside the tile
         const uint32_t dst = e_addr + (rr >> 3) * kLBO + (rr & 7) * 2;
         for (int bl = 0; bl < pack; ++bl) {         // original row rr * pack + bl -> E columns 3*bl .. 3*bl+2
           const int sub = rr * pack + bl;
@@ -459,7 +459,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     if (lane == 0) {
-      double* ys = side + (size_t)blockIdx.x * kTcSideDoubles;
+      double* ys = side + (size_t)blockIdx.x * kTcSideDoubles + 3 * (warp - 2);
       ys[0] = sy; ys[1] = syy; ys[2] = cnt;
     }
   } else if (warp >= 4 && warp < 8) {
@@ -694,7 +694,7 @@ tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ sid
   } else if (idx < kTcAccElems + 3) {
     const int k = idx - kTcAccElems;
     double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k];
+    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k] + side[(size_t)c * kTcSideDoubles + 3 + k];
     red[idx] = s;
   }
 }
