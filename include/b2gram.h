@@ -45,6 +45,8 @@ extern "C" {
 #define B2_KERNEL_AUTO 0   /* tcgen05 path when shape/alignment allow, else CUDA-core */
 #define B2_KERNEL_SIMT 1   /* fp64-accumulating CUDA-core kernel (any D <= 128)       */
 #define B2_KERNEL_TCGEN05 2 /* TMA -> smem -> bf16 hi/lo split -> tcgen05.mma -> TMEM   */
+/* tcgen05 path requirements: 4 <= d <= 128, row bytes and row pitch multiples of 16, X / y / row_mask 16-byte
+ * aligned, n_rows >= 64.  Contiguous rows with d == 32 or 64 are packed 4 / 2 per 128-wide super-row. */
 
 /* operand precision of the tcgen05 Gram kernel (b2_ctx_set_precision) */
 #define B2_PRECISION_SPLIT 0 /* bf16 hi + lo operands (16 mantissa bits), default: coef error ~2e-6 at any n */
@@ -144,8 +146,8 @@ int b2_comm_barrier(b2_ctx* ctx);
 
 /* ---- timing (CUDA events on the ctx stream) ---------------------------------------------------------
  * b2_timer_start/stop bracket any sequence of calls; *_ms is device time between the two events.
- * b2_last_kernel_ms: device time of the dominant Gram kernel launches inside the most recent
- * b2_gram_accumulate (sum over its launches), and how many kernels that call launched. */
+ * b2_last_kernel_ms: summed device time of the tcgen05 Gram kernel launches (one CUDA-event pair each, at most
+ * the 64 most recent) since the previous call to this function, and how many launches that sum covers. */
 int b2_timer_start(b2_ctx* ctx);
 int b2_timer_stop(b2_ctx* ctx, double* ms_out);
 int b2_last_kernel_ms(b2_ctx* ctx, double* gram_ms_out, int* launches_out);
