@@ -196,7 +196,8 @@ def workload_config(n_gpus: int, x_kind: str) -> dict:
     return {"workload": (f"{rows * n_gpus} rows x {D} features ({rows} per GPU, row-sharded), X {x_kind} + y fp32 "
                          f"resident in HBM; BASELINE.json configs[{1 if n_gpus == 1 else 2}]"),
             "rows_per_gpu": rows, "features": D, "x_storage": x_kind,
-            "parallelism": f"row-shard x{n_gpus}, one NCCL all-reduce of the (D+2)^2 fp64 statistic",
+            "parallelism": f"row-shard x{n_gpus}, one all-reduce of the (D+2)^2 fp64 statistic per fit (peer-memory one-shot "
+                           f"exchange over NVLink; NCCL all-reduce when B2_NO_P2P=1)",
             "l2": "inputs larger than L2 (5.2 GB per pass vs 126 MB)"}
 
 
@@ -243,6 +244,11 @@ def main() -> None:
         uid = [b2.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
+        if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
+            # one-shot peer-memory exchange of S (NVLink stores + flags) instead of an NCCL launch per step
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.comm_p2p_export())
+            ctx.comm_p2p_attach(world, rank, handles)
 
     rows = args.rows or (ROWS_N1 if world == 1 else ROWS_PER_GPU_MULTI)
     kind = args.x_dtype

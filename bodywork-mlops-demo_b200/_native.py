@@ -59,6 +59,8 @@ _SIGNATURES = {
     "b2_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
     "b2_comm_destroy": (C.c_int, [_vp]),
     "b2_comm_barrier": (C.c_int, [_vp]),
+    "b2_comm_p2p_export": (C.c_int, [_vp, C.c_char_p]),
+    "b2_comm_p2p_attach": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
     "b2_timer_start": (C.c_int, [_vp]),
     "b2_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "b2_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -360,6 +362,20 @@ class Context:
     def comm_init(self, n_ranks: int, rank: int, uid: bytes) -> None:
         _check(load().b2_comm_init(self._h, int(n_ranks), int(rank), C.create_string_buffer(uid, 128)),
                "b2_comm_init")
+
+    def comm_p2p_export(self) -> bytes:
+        """CUDA-IPC handle (64 bytes) of this rank's exchange buffer for the one-shot peer-memory all-reduce."""
+        buf = C.create_string_buffer(64)
+        _check(load().b2_comm_p2p_export(self._h, buf), "b2_comm_p2p_export")
+        return buf.raw
+
+    def comm_p2p_attach(self, n_ranks: int, rank: int, handles) -> None:
+        """``handles``: the exported handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * n_ranks:
+            raise RuntimeError("need one 64-byte handle per rank")
+        _check(load().b2_comm_p2p_attach(self._h, int(n_ranks), int(rank), C.create_string_buffer(blob, len(blob))),
+               "b2_comm_p2p_attach")
 
     def comm_barrier(self) -> None:
         _check(load().b2_comm_barrier(self._h), "b2_comm_barrier")

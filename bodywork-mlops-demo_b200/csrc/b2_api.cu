@@ -210,6 +210,10 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->comm != nullptr) b2_comm_destroy(ctx);
+  if (ctx->p2p_ready)
+    for (int r = 0; r < ctx->n_ranks; ++r)
+      if (r != ctx->rank && ctx->xchg_peer[r] != nullptr) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+  if (ctx->xchg != nullptr) cudaFree(ctx->xchg);
   void* bufs[] = {ctx->S, ctx->tc_part, ctx->tc_side, ctx->tc_red, ctx->shift, ctx->simt_part, ctx->score_part,
                   ctx->coef_dev, ctx->solve_out, ctx->stage_x[0], ctx->stage_x[1], ctx->stage_y[0], ctx->stage_y[1],
                   ctx->stage_m[0], ctx->stage_m[1]};
@@ -350,6 +354,7 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
 int b2_gram_allreduce(b2_ctx* ctx) {
   if (int r = use_device(ctx)) return r;
   if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
+  if (ctx->n_ranks > 1 && ctx->p2p_ready) return launch_p2p_allreduce(ctx);   // peer-memory one-shot exchange
   if (ctx->n_ranks == 1 || ctx->comm == nullptr) return B2_OK;
   NcclApi* api = nccl();
   if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
@@ -546,6 +551,43 @@ int b2_comm_destroy(b2_ctx* ctx) {
   ctx->comm = nullptr;
   ctx->n_ranks = 1;
   ctx->rank = 0;
+  return B2_OK;
+}
+
+int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out) {
+  if (int r = use_device(ctx)) return r;
+  if (handle_out == nullptr) { set_error("handle_out is null"); return B2_E_ARG; }
+  if (ctx->xchg == nullptr) {
+    B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->xchg), kXchgBytes));
+    B2_CUDA(cudaMemset(ctx->xchg, 0, kXchgBytes));
+    B2_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  return B2_OK;
+}
+
+int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles) {
+  if (int r = use_device(ctx)) return r;
+  if (n_ranks < 2 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks || handles == nullptr || ctx->xchg == nullptr) {
+    set_error("b2_comm_p2p_attach: bad arguments (2..%d ranks; call b2_comm_p2p_export first)", kMaxRanks);
+    return B2_E_ARG;
+  }
+  if (ctx->p2p_ready) { set_error("peer exchange already attached"); return B2_E_STATE; }
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == rank) { ctx->xchg_peer[r] = ctx->xchg; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    B2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->xchg_peer[r] = static_cast<double*>(p);
+  }
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  ctx->xchg_epoch = 0;
+  ctx->p2p_ready = true;
   return B2_OK;
 }
 

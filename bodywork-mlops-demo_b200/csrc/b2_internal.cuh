@@ -13,6 +13,10 @@ namespace b2 {
 constexpr int kMaxD = B2_MAX_D;          // 128 features
 constexpr int kMaxS = kMaxD + 2;         // 130: features, ones, y
 constexpr int kKernelEventPairs = 64;
+constexpr int kMaxRanks = 8;
+constexpr size_t kXchgSlotDoubles = (size_t)kMaxS * kMaxS;                 // one rank's S
+constexpr size_t kXchgDataDoubles = 2 * kMaxRanks * kXchgSlotDoubles;       // two epochs (parity) x ranks
+constexpr size_t kXchgBytes = kXchgDataDoubles * sizeof(double) + 256;      // + flags[8] (u32) + ticket
 
 // ---- tcgen05 Gram kernel geometry (gram_tc.cu) ------------------------------------------
 constexpr int kTcRows = 64;              // rows of X per pipeline stage (4 MMA K-steps of 16)
@@ -90,6 +94,11 @@ struct b2_ctx {
   // NCCL
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // one-shot peer-memory all-reduce of S (p2p.cu): exchange buffer exported over CUDA IPC
+  double* xchg = nullptr;              // [2 parities][kMaxRanks][kMaxS*kMaxS] slots, then flags / ticket words
+  double* xchg_peer[8] = {nullptr};    // this rank's view of every rank's exchange buffer (own entry == xchg)
+  bool p2p_ready = false;
+  unsigned int xchg_epoch = 0;
 };
 
 namespace b2 {
@@ -104,6 +113,7 @@ int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept);
 int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept);
 int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx,
                  const float* y, const uint8_t* mask, int keep, float* yhat, bool first_block);
+int launch_p2p_allreduce(b2_ctx* ctx);
 int launch_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int d, int64_t ldx,
                  int x_dtype, double alpha, double beta, double sigma, void* X, float* y);
 

@@ -143,6 +143,12 @@ int b2_comm_unique_id(char* id_out /* 128 bytes */);
 int b2_comm_init(b2_ctx* ctx, int n_ranks, int rank, const char* id /* 128 bytes */);
 int b2_comm_destroy(b2_ctx* ctx);
 int b2_comm_barrier(b2_ctx* ctx);
+/* Optional one-shot peer-memory exchange for b2_gram_allreduce (2..8 ranks of one NVLink box): every rank exports
+ * the CUDA-IPC handle of its exchange buffer (64 bytes), the caller gathers the handles of all ranks in rank
+ * order and attaches them.  Once attached, b2_gram_allreduce stores S into every peer's buffer over NVLink and
+ * sums the n slots in rank order (no NCCL launch; bit-identical S on every rank); NCCL stays the fallback. */
+int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out /* 64 bytes */);
+int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles /* n_ranks x 64 bytes */);
 
 /* ---- timing (CUDA events on the ctx stream) ---------------------------------------------------------
  * b2_timer_start/stop bracket any sequence of calls; *_ms is device time between the two events.
