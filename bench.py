@@ -246,9 +246,18 @@ def main() -> None:
         ctx.comm_init(world, rank, uid[0])
         if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
             # one-shot peer-memory exchange of S (NVLink stores + flags) instead of an NCCL launch per step
-            handles = [None] * world
-            dist.all_gather_object(handles, ctx.comm_p2p_export())
-            ctx.comm_p2p_attach(world, rank, handles)
+            ok = True
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.comm_p2p_export())
+                ctx.comm_p2p_attach(world, rank, handles)
+            except Exception as exc:   # e.g. CUDA IPC unavailable in this container: every rank falls back to NCCL
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+                ok = False
+            oks = [None] * world
+            dist.all_gather_object(oks, ok)
+            if not all(oks):
+                ctx.comm_p2p_detach()
 
     rows = args.rows or (ROWS_N1 if world == 1 else ROWS_PER_GPU_MULTI)
     kind = args.x_dtype

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b2_comm_barrier": (C.c_int, [_vp]),
     "b2_comm_p2p_export": (C.c_int, [_vp, C.c_char_p]),
     "b2_comm_p2p_attach": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
+    "b2_comm_p2p_detach": (C.c_int, [_vp]),
     "b2_timer_start": (C.c_int, [_vp]),
     "b2_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "b2_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -376,6 +377,9 @@ class Context:
             raise RuntimeError("need one 64-byte handle per rank")
         _check(load().b2_comm_p2p_attach(self._h, int(n_ranks), int(rank), C.create_string_buffer(blob, len(blob))),
                "b2_comm_p2p_attach")
+
+    def comm_p2p_detach(self) -> None:
+        _check(load().b2_comm_p2p_detach(self._h), "b2_comm_p2p_detach")
 
     def comm_barrier(self) -> None:
         _check(load().b2_comm_barrier(self._h), "b2_comm_barrier")

@@ -210,9 +210,7 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->comm != nullptr) b2_comm_destroy(ctx);
-  if (ctx->p2p_ready)
-    for (int r = 0; r < ctx->n_ranks; ++r)
-      if (r != ctx->rank && ctx->xchg_peer[r] != nullptr) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+  b2_comm_p2p_detach(ctx);
   if (ctx->xchg != nullptr) cudaFree(ctx->xchg);
   void* bufs[] = {ctx->S, ctx->tc_part, ctx->tc_side, ctx->tc_red, ctx->shift, ctx->simt_part, ctx->score_part,
                   ctx->coef_dev, ctx->solve_out, ctx->stage_x[0], ctx->stage_x[1], ctx->stage_y[0], ctx->stage_y[1],
@@ -588,6 +586,18 @@ int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles) 
   ctx->rank = rank;
   ctx->xchg_epoch = 0;
   ctx->p2p_ready = true;
+  return B2_OK;
+}
+
+int b2_comm_p2p_detach(b2_ctx* ctx) {
+  if (ctx == nullptr) { set_error("null context"); return B2_E_ARG; }
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->p2p_ready)
+    for (int r = 0; r < ctx->n_ranks; ++r)
+      if (r != ctx->rank && ctx->xchg_peer[r] != nullptr) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+  for (int r = 0; r < kMaxRanks; ++r) ctx->xchg_peer[r] = nullptr;
+  ctx->p2p_ready = false;
   return B2_OK;
 }
 

@@ -149,6 +149,7 @@ int b2_comm_barrier(b2_ctx* ctx);
  * sums the n slots in rank order (no NCCL launch; bit-identical S on every rank); NCCL stays the fallback. */
 int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out /* 64 bytes */);
 int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles /* n_ranks x 64 bytes */);
+int b2_comm_p2p_detach(b2_ctx* ctx); /* back to the NCCL all-reduce (all ranks must detach together) */
 
 /* ---- timing (CUDA events on the ctx stream) ---------------------------------------------------------
  * b2_timer_start/stop bracket any sequence of calls; *_ms is device time between the two events.
