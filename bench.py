@@ -246,14 +246,20 @@ def main() -> None:
         ctx.comm_init(world, rank, uid[0])
         if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
             # one-shot peer-memory exchange of S (NVLink stores + flags) instead of an NCCL launch per step
-            ok = True
             try:
-                handles = [None] * world
-                dist.all_gather_object(handles, ctx.comm_p2p_export())
-                ctx.comm_p2p_attach(world, rank, handles)
-            except Exception as exc:   # e.g. CUDA IPC unavailable in this container: every rank falls back to NCCL
-                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using NCCL", file=sys.stderr)
-                ok = False
+                mine = ctx.comm_p2p_export()
+            except Exception as exc:   # e.g. CUDA IPC unavailable in this container
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc})", file=sys.stderr)
+                mine = None
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)          # every rank takes part in both collectives
+            ok = all(h is not None for h in handles)
+            if ok:
+                try:
+                    ctx.comm_p2p_attach(world, rank, handles)
+                except Exception as exc:
+                    print(f"[bench] rank {rank}: attaching peer buffers failed ({exc}); using NCCL", file=sys.stderr)
+                    ok = False
             oks = [None] * world
             dist.all_gather_object(oks, ok)
             if not all(oks):
