@@ -61,6 +61,9 @@ class B200LinearRegression:
             # rank deficient and alpha == 0: the minimum-norm solution gelsd would return (device Jacobi)
             spectral = ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
             coef, b0 = spectral[0], spectral[1]
+        if not (np.all(np.isfinite(coef)) and np.isfinite(b0)):
+            # sklearn's check_array refuses such input up front; here it shows up in the statistic
+            raise ValueError("Input X or y contains NaN, infinity or a value too large for dtype('float32').")
         if with_spectrum and spectral is None:
             spectral = ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
         self.coef_ = coef

@@ -560,3 +560,16 @@ def test_single_bf16_operand_mode_meets_the_contract_at_large_n(ctx, kind):
     assert errs[b2.PRECISION_SPLIT] < COEF_TOL
     assert errs[b2.PRECISION_BF16] < 1e-4
     X.free(); y.free()
+
+
+def test_non_finite_input_is_refused_like_sklearn(ctx):
+    X, y = orc.generate_dataset(5000, 8, seed=3, dtype=np.float32)
+    X[17, 3] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        b2.B200LinearRegression(ctx=ctx).fit(X, y)
+    X[17, 3] = 1.0
+    y[5] = np.inf
+    with pytest.raises(ValueError, match="NaN"):
+        b2.B200LinearRegression(ctx=ctx).fit(X, y)
+    y[5] = 0.0
+    assert np.all(np.isfinite(b2.B200LinearRegression(ctx=ctx).fit(X, y).coef_))     # the context is still usable
