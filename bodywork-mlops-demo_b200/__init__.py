@@ -9,11 +9,11 @@ Import name: ``bodywork_mlops_demo_b200`` (a shim package that points here -- th
     stage_1_train_model    drop-in for mlops_simulation/stage_1_train_model.py
 """
 from . import _native as native
-from ._native import (BF16, F32, KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05, PRECISION_BF16, PRECISION_SPLIT, Context,
+from ._native import (BF16, F32, KERNEL_AUTO, KERNEL_NARROW, KERNEL_SIMT, KERNEL_TCGEN05, PRECISION_BF16, PRECISION_SPLIT, Context,
                       DeviceArray, PinnedArray)
 from .estimator import B200LinearRegression, default_context
 from . import sharding, tranche_io  # noqa: F401
 
 __all__ = ["native", "Context", "DeviceArray", "PinnedArray", "B200LinearRegression", "default_context",
-           "F32", "BF16", "KERNEL_AUTO", "KERNEL_SIMT", "KERNEL_TCGEN05", "PRECISION_SPLIT", "PRECISION_BF16"]
+           "F32", "BF16", "KERNEL_AUTO", "KERNEL_SIMT", "KERNEL_TCGEN05", "KERNEL_NARROW", "PRECISION_SPLIT", "PRECISION_BF16"]
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ from . import build as _build
 
 F32, BF16 = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
-KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05 = 0, 1, 2
+KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05, KERNEL_NARROW = 0, 1, 2, 3
 PRECISION_SPLIT, PRECISION_BF16 = 0, 1
 E_SINGULAR = -4
 MAX_D = 128

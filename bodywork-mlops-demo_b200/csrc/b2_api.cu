@@ -91,12 +91,23 @@ int gram_block(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t 
   if (n == 0) return B2_OK;
   const bool tc_ok = gram_tc_supported(X, x_dtype, y, n, d, ldx) &&
                      (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+  const bool nw_ok = gram_narrow_supported(X, x_dtype, y, n, d, ldx, mask);
   int mode = ctx->kernel_mode;
   if (mode == B2_KERNEL_TCGEN05 && !tc_ok) {
     set_error("tcgen05 path needs d%%4==0 (fp32) / d%%8==0 (bf16), 16-byte aligned X/y/mask/row pitch, n>=32");
     return B2_E_UNSUPPORTED;
   }
-  if (mode == B2_KERNEL_AUTO) mode = (tc_ok && n >= 2048) ? B2_KERNEL_TCGEN05 : B2_KERNEL_SIMT;
+  if (mode == B2_KERNEL_NARROW && !nw_ok) {
+    set_error("narrow path needs d<=16, contiguous rows (ldx==d) and 16-byte aligned X/y/mask");
+    return B2_E_UNSUPPORTED;
+  }
+  if (mode == B2_KERNEL_AUTO) {
+    // narrow rows stream through the CUDA-core pipeline (HBM-bound); wide rows go to the tensor core;
+    // tiny tranches (the reference's 1 440-row day) and odd layouts stay on the exact fp64 kernel
+    if (nw_ok && n >= 4096) mode = B2_KERNEL_NARROW;
+    else mode = (tc_ok && n >= 2048) ? B2_KERNEL_TCGEN05 : B2_KERNEL_SIMT;
+  }
+  if (mode == B2_KERNEL_NARROW) return launch_gram_narrow(ctx, X, x_dtype, y, n, d, ldx, mask, keep);
   if (mode == B2_KERNEL_TCGEN05) return launch_gram_tc(ctx, X, x_dtype, y, n, d, ldx, mask, keep);
   return launch_gram_simt(ctx, X, x_dtype, y, n, d, ldx, mask, keep);
 }
@@ -249,7 +260,7 @@ int b2_ctx_info(b2_ctx* ctx, char* name, int name_cap, int* sm_count, size_t* hb
 }
 
 int b2_ctx_set_kernel(b2_ctx* ctx, int kernel) {
-  if (ctx == nullptr || kernel < B2_KERNEL_AUTO || kernel > B2_KERNEL_TCGEN05) { set_error("bad kernel id"); return B2_E_ARG; }
+  if (ctx == nullptr || kernel < B2_KERNEL_AUTO || kernel > B2_KERNEL_NARROW) { set_error("bad kernel id"); return B2_E_ARG; }
   ctx->kernel_mode = kernel;
   return B2_OK;
 }

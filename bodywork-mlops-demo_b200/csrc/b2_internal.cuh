@@ -109,6 +109,10 @@ int launch_gram_simt(b2_ctx* ctx, const void* X, int x_dtype, const float* y, in
 bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx);
 int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
                    int64_t ldx, const uint8_t* mask, int keep);
+bool gram_narrow_supported(const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
+                           const uint8_t* mask);
+int launch_gram_narrow(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
+                       int64_t ldx, const uint8_t* mask, int keep);
 int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept);
 int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept);
 int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx,

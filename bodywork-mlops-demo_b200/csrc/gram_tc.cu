@@ -33,6 +33,7 @@
 #include <stdlib.h>
 
 #include "b2_internal.cuh"
+#include "b2_ptx.cuh"
 
 namespace b2 {
 namespace {
@@ -77,46 +78,6 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTc
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// Wait with a hardware suspend hint (the thread sleeps inside try_wait and is woken by the arrive, so
-// waiting warps do not burn issue slots).  Bounded: a protocol bug must end in a trap (a clean launch
-// failure), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 20000u) {
-  uint32_t done = 0;
-  uint64_t t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(hint_ns)
-        : "memory");
-    if (done) break;
-    const uint64_t now = globaltimer_ns();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000ull) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -189,36 +150,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint32_t (&v)[
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_shared_u8(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-// one element of the raw tile as fp32 (T = float: 4-byte load; T = bf16: 2-byte load, widen)
-template <typename T>
-__device__ __forceinline__ float raw_ld_shared(uint32_t addr);
-template <>
-__device__ __forceinline__ float raw_ld_shared<float>(uint32_t addr) { return ld_shared_f32(addr); }
-template <>
-__device__ __forceinline__ float raw_ld_shared<__nv_bfloat16>(uint32_t addr) {
-  unsigned short h;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
-  return __uint_as_float(((uint32_t)h) << 16);
-}
-template <typename T>
-__device__ __forceinline__ float raw_ld_global(const T* p);
-template <>
-__device__ __forceinline__ float raw_ld_global<float>(const float* p) { return __ldg(p); }
-template <>
-__device__ __forceinline__ float raw_ld_global<__nv_bfloat16>(const __nv_bfloat16* p) {
-  return __bfloat162float(*p);
-}
-
 // bf16 split of two fp32 values: hi = rn(v), lo = rn(v - hi), packed (element 0 in the low half)
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);

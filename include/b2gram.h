@@ -45,6 +45,7 @@ extern "C" {
 #define B2_KERNEL_AUTO 0   /* tcgen05 path when shape/alignment allow, else CUDA-core */
 #define B2_KERNEL_SIMT 1   /* fp64-accumulating CUDA-core kernel (any D <= 128)       */
 #define B2_KERNEL_TCGEN05 2 /* TMA -> smem -> bf16 hi/lo split -> tcgen05.mma -> TMEM   */
+#define B2_KERNEL_NARROW 3  /* D <= 16: TMA bulk-copy pipeline -> fp32 FMA on CUDA cores */
 /* tcgen05 path requirements: 4 <= d <= 128, row bytes and row pitch multiples of 16, X / y / row_mask 16-byte
  * aligned, n_rows >= 64.  Contiguous rows with d == 32 or 64 are packed 4 / 2 per 128-wide super-row. */
 

@@ -80,6 +80,91 @@ def test_tcgen05_equals_simt_on_device(ctx):
     assert _rel(a, b) < 2e-6
 
 
+# ------------------------------------------------------------------------------------------------
+# narrow rows (D <= 16): the CUDA-core streaming kernel behind the TMA bulk-copy pipeline
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["f32", "bf16"])
+@pytest.mark.parametrize("n,d", [(4096, 1), (50_001, 1), (33_333, 2), (20_000, 3), (70_007, 4), (30_000, 5),
+                                 (100_003, 8), (9_000, 9), (25_000, 12), (60_001, 16)])
+def test_narrow_gram_matches_oracle(ctx, n, d, kind):
+    X, y = orc.generate_dataset(n, d, seed=n + d, dtype=np.float32)
+    if kind == "bf16":
+        bits = b2.native.to_bf16_bits(X)
+        X = b2.native.from_bf16_bits(bits)
+        S = _gram(ctx, bits, y, b2.KERNEL_NARROW, kind="bf16")
+    else:
+        S = _gram(ctx, X, y, b2.KERNEL_NARROW)
+    So = orc.gram_stats(X, y)
+    assert S[d, d] == n                                    # row count is exact
+    assert _rel(S, So) < 1e-6                              # fp32 FMA chains folded into fp64
+    assert np.array_equal(S, S.T)
+    ctx.gram_import(S)
+    coef, b0 = ctx.solve()
+    fo = orc.fit_from_stats(So)
+    assert np.max(np.abs(coef - fo["coef"])) < COEF_TOL
+    assert abs(b0 - fo["intercept"]) < INTERCEPT_TOL
+
+
+@pytest.mark.parametrize("d,keep", [(1, 1), (8, 1), (8, 0), (16, 1), (11, 0)])
+def test_narrow_row_mask_equals_gather(ctx, d, keep):
+    X, y = orc.generate_dataset(41_017, d, seed=31 + d, dtype=np.float32)
+    mask = s1.split_mask(X.shape[0])
+    S = _gram(ctx, X, y, b2.KERNEL_NARROW, mask=mask, keep=keep)
+    So = orc.gram_stats(X[mask == keep], y[mask == keep])
+    assert S[d, d] == int((mask == keep).sum())
+    assert _rel(S, So) < 1e-6
+
+
+def test_narrow_is_deterministic_additive_and_the_auto_choice(ctx):
+    X, y = orc.generate_dataset(120_000, 8, seed=12, dtype=np.float32)
+    a = _gram(ctx, X, y, b2.KERNEL_NARROW)
+    assert np.array_equal(a, _gram(ctx, X, y, b2.KERNEL_NARROW))
+    assert np.array_equal(a, _gram(ctx, X, y, b2.KERNEL_AUTO))       # AUTO takes the narrow kernel for D <= 16
+    ctx.set_kernel(b2.KERNEL_NARROW)
+    ctx.gram_reset(8)
+    for lo, hi in ((0, 50_000), (50_000, 120_000)):
+        Xd, yd = ctx.to_device(X[lo:hi]), ctx.to_device(y[lo:hi])
+        ctx.gram_accumulate(Xd, yd)
+        Xd.free(); yd.free()
+    parts = ctx.gram_export()
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    assert parts[8, 8] == 120_000 and _rel(parts, a) < 1e-7
+    assert _rel(a, _gram(ctx, X, y, b2.KERNEL_SIMT)) < 1e-6
+
+
+def test_narrow_badly_offset_columns_keep_their_digits(ctx):
+    """Column means 1e4 times the spread: the per-column shift is what keeps fp32 products usable."""
+    rng = np.random.RandomState(4)
+    n, d = 200_000, 4
+    X = (10_000.0 + rng.normal(0.0, 1.0, size=(n, d))).astype(np.float32)
+    y = (3.0 + X.astype(np.float64) @ np.array([0.5, -1.0, 2.0, 0.25]) + rng.normal(0, 0.1, n)).astype(np.float32)
+    S = _gram(ctx, X, y, b2.KERNEL_NARROW)
+    fo = orc.fit_from_stats(orc.gram_stats(X, y))
+    ctx.gram_import(S)
+    coef, _ = ctx.solve()
+    assert np.max(np.abs(coef - fo["coef"])) < 1e-4
+
+
+@pytest.mark.parametrize("d", [1, 8, 16])
+def test_narrow_large_n_agrees_with_the_other_kernels(ctx, d):
+    n = 20_000_000 + 77
+    X, y = ctx.synth(n, d, seed=99)
+    res = {}
+    for kernel in [b2.KERNEL_NARROW] + ([b2.KERNEL_TCGEN05] if d >= 4 else []):   # tcgen05 zero-pads D to 128
+        ctx.set_kernel(kernel)
+        ctx.gram_reset(d)
+        ctx.gram_accumulate(X, y)
+        res[kernel] = (ctx.gram_export(), ctx.solve())
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    S, (coef, b0) = res[b2.KERNEL_NARROW]
+    assert S[d, d] == n
+    assert np.max(np.abs(coef - 0.5)) < 5e-4 and abs(b0 - 1.0) < 0.05      # the generator's truth (stage_3...:36-41)
+    if b2.KERNEL_TCGEN05 in res:
+        S2, (coef2, _) = res[b2.KERNEL_TCGEN05]
+        assert _rel(S, S2) < 2e-6 and np.max(np.abs(coef - coef2)) < COEF_TOL
+    X.free(); y.free()
+
+
 @pytest.mark.parametrize("drain", [64, 1024, 8192, 65536])
 def test_drain_interval_does_not_change_the_fit(ctx, drain):
     X, y = orc.generate_dataset(150_000, 128, seed=5, dtype=np.float32)

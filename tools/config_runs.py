@@ -6,7 +6,7 @@
   c4      configs[3]: D = 32 rows streamed from pinned host DRAM through the C-ABI (B2_MEM_HOST); 200 M rows
           (26 GB pinned) stand in for 1 B (132 GB): the path is PCIe-bound, the rate does not depend on N
   c5      configs[4]: 30-day concept-drift replay, D = 1 reference-faithful tranches and a 1 M x 128 variant
-  shapes  device-resident Gram-kernel rate for D in {8, 32, 64, 128} x {f32, bf16}
+  shapes  device-resident Gram-kernel rate for D in {1, 8, 16, 32, 64, 128} x {f32, bf16}
 """
 from __future__ import annotations
 
@@ -26,7 +26,7 @@ out = {}
 
 
 def gram_rate(ctx, X, y, n, d, kind, reps=6):
-    ctx.set_kernel(b2.KERNEL_TCGEN05)
+    ctx.set_kernel(b2.KERNEL_AUTO)      # D <= 16: CUDA-core streaming kernel; wider: tcgen05
     best_k, best_t = 1e9, 1e9
     for _ in range(reps):
         ctx.gram_reset(d)
@@ -121,11 +121,9 @@ def c5(ctx):
 
 def shapes(ctx):
     res = []
-    for d in (8, 32, 64, 128):
+    for d in (1, 8, 16, 32, 64, 128):
         for kind in ("f32", "bf16"):
-            if kind == "bf16" and d % 8:
-                continue
-            n = 40_000_000 if d <= 32 else 10_000_000
+            n = 200_000_000 if d == 1 else 40_000_000 if d <= 32 else 10_000_000
             X, y = ctx.synth(n, d, seed=5, kind=kind)
             ctx.sync()
             r = gram_rate(ctx, X, y, n, d, kind)
