@@ -167,28 +167,8 @@ int b2_device_count(int* n_out) {
   return B2_OK;
 }
 
-int b2_ctx_create(int device, b2_ctx** out) {
-  if (out == nullptr) { set_error("out is null"); return B2_E_ARG; }
-  *out = nullptr;
-  int n = 0;
-  if (b2_device_count(&n) != B2_OK || n == 0) {
-    set_error("no usable CUDA device (libb2gram has no CPU fallback)");
-    return B2_E_CUDA;
-  }
-  if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return B2_E_ARG; }
-  B2_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  B2_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    set_error("device %d is sm_%d%d; libb2gram is built for sm_100a only", device, prop.major, prop.minor);
-    return B2_E_UNSUPPORTED;
-  }
-  b2_ctx* ctx = new (std::nothrow) b2_ctx();
-  if (ctx == nullptr) { set_error("out of host memory"); return B2_E_STATE; }
-  ctx->device = device;
-  ctx->sm_count = prop.multiProcessorCount;
-  ctx->hbm_bytes = prop.totalGlobalMem;
-  snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+// streams, events and device scratch of a fresh context (b2_ctx_create destroys the context if this fails)
+static int ctx_allocate(b2_ctx* ctx) {
   B2_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   B2_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreate(&ctx->ev_t0));
@@ -212,6 +192,35 @@ int b2_ctx_create(int device, b2_ctx** out) {
   B2_CUDA(cudaMemset(ctx->S, 0, sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMemset(ctx->tc_side, 0, sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
   B2_CUDA(cudaMemset(ctx->tc_red, 0, sizeof(double) * (kTcAccElems + 16 + kMaxD + 8)));
+  return B2_OK;
+}
+
+int b2_ctx_create(int device, b2_ctx** out) {
+  if (out == nullptr) { set_error("out is null"); return B2_E_ARG; }
+  *out = nullptr;
+  int n = 0;
+  if (b2_device_count(&n) != B2_OK || n == 0) {
+    set_error("no usable CUDA device (libb2gram has no CPU fallback)");
+    return B2_E_CUDA;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return B2_E_ARG; }
+  B2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libb2gram is built for sm_100a only", device, prop.major, prop.minor);
+    return B2_E_UNSUPPORTED;
+  }
+  b2_ctx* ctx = new (std::nothrow) b2_ctx();
+  if (ctx == nullptr) { set_error("out of host memory"); return B2_E_STATE; }
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->hbm_bytes = prop.totalGlobalMem;
+  snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+  if (int r = ctx_allocate(ctx)) {   // streams, events, scratch: release whatever was created before the failure
+    b2_ctx_destroy(ctx);
+    return r;
+  }
   *out = ctx;
   return B2_OK;
 }
@@ -232,14 +241,14 @@ int b2_ctx_destroy(b2_ctx* ctx) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
   }
-  for (int i = 0; i < kKernelEventPairs; ++i) {
-    cudaEventDestroy(ctx->ev_k[i][0]);
-    cudaEventDestroy(ctx->ev_k[i][1]);
-  }
-  cudaEventDestroy(ctx->ev_t0);
-  cudaEventDestroy(ctx->ev_t1);
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < kKernelEventPairs; ++i)
+    for (int e = 0; e < 2; ++e)
+      if (ctx->ev_k[i][e] != nullptr) cudaEventDestroy(ctx->ev_k[i][e]);
+  if (ctx->ev_t0 != nullptr) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1 != nullptr) cudaEventDestroy(ctx->ev_t1);
+  if (ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream != nullptr) cudaStreamDestroy(ctx->copy_stream);
+  cudaGetLastError();   // a half-built context may have left a sticky-free error code behind
   delete ctx;
   return B2_OK;
 }
@@ -344,9 +353,8 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
   if (int r = ensure_staging(ctx)) return r;
   const int es = x_dtype == B2_F32 ? 4 : 2;
   int64_t blk = 0;
-  for (int64_t r0 = 0; r0 < n_rows; r0 += ctx->stage_rows, ++blk) {
-    const int buf = (int)(blk & 1);
-    const int64_t rows = (n_rows - r0 < ctx->stage_rows) ? n_rows - r0 : ctx->stage_rows;
+  int rc = B2_OK;
+  auto step = [&](int64_t r0, int buf, int64_t rows) -> int {
     if (blk >= 2) B2_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
     if (int r = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx)) return r;
     B2_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
@@ -355,8 +363,16 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
                            row_mask ? ctx->stage_m[buf] : nullptr, mask_keep))
       return r;
     B2_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    return B2_OK;
+  };
+  for (int64_t r0 = 0; r0 < n_rows && rc == B2_OK; r0 += ctx->stage_rows, ++blk) {
+    const int64_t rows = (n_rows - r0 < ctx->stage_rows) ? n_rows - r0 : ctx->stage_rows;
+    rc = step(r0, (int)(blk & 1), rows);
   }
-  B2_CUDA(cudaStreamSynchronize(ctx->copy_stream));  // caller may reuse its host buffers on return
+  // the caller may reuse its host buffers on return -- also when a block failed
+  const cudaError_t drained = cudaStreamSynchronize(ctx->copy_stream);
+  if (rc != B2_OK) return rc;
+  B2_CUDA(drained);
   return B2_OK;
 }
 
@@ -459,11 +475,18 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
   } else {
     if (int r = ensure_staging(ctx)) return r;
     const int es = x_dtype == B2_F32 ? 4 : 2;
-    // yhat for a block is produced into the (otherwise unused) tail of the y staging buffer? no:
-    // y staging holds y; reuse the mask staging only for masks.  A dedicated device block for yhat:
+    // predictions of a staged block land in a device block of their own and are copied back behind the kernel
     float* yhat_dev[2] = {nullptr, nullptr};
-    if (yhat != nullptr)
-      for (int b = 0; b < 2; ++b) B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&yhat_dev[b]), (size_t)ctx->stage_rows * 4));
+    if (yhat != nullptr) {
+      for (int b = 0; b < 2; ++b) {
+        if (cudaMalloc(reinterpret_cast<void**>(&yhat_dev[b]), (size_t)ctx->stage_rows * 4) != cudaSuccess) {
+          cudaGetLastError();
+          if (yhat_dev[0] != nullptr) cudaFree(yhat_dev[0]);
+          set_error("out of device memory for the prediction staging blocks");
+          return B2_E_CUDA;
+        }
+      }
+    }
     int64_t blk = 0;
     int rc = B2_OK;
     for (int64_t r0 = 0; r0 < n_rows && rc == B2_OK; r0 += ctx->stage_rows, ++blk) {

@@ -165,6 +165,40 @@ def test_narrow_large_n_agrees_with_the_other_kernels(ctx, d):
     X.free(); y.free()
 
 
+def _random_case(i):
+    rng = np.random.RandomState(1000 + i)
+    d = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 16, 20, 32, 33, 48, 64, 96, 100, 128]))
+    n = int(rng.choice([1, 2, 63, 64, 65, 1000, 2047, 2048, 4095, 4096, 5000, 9999, 30_000, 70_001]))
+    kind = "bf16" if (rng.rand() < 0.3 and d % 8 == 0) else "f32"
+    masked = rng.rand() < 0.4
+    return n, d, kind, masked
+
+
+@pytest.mark.parametrize("i", range(48))
+def test_randomized_shapes_through_the_auto_dispatch(ctx, i):
+    """Whatever kernel AUTO picks (exact fp64 / narrow / tcgen05 / packed), the statistic is the oracle's."""
+    n, d, kind, masked = _random_case(i)
+    X, y = orc.generate_dataset(n, d, seed=i, dtype=np.float32)
+    mask = (np.random.RandomState(i).rand(n) < 0.8).astype(np.uint8) if masked else None
+    if kind == "bf16":
+        bits = b2.native.to_bf16_bits(X)
+        X = b2.native.from_bf16_bits(bits)
+        S = _gram(ctx, bits, y, b2.KERNEL_AUTO, mask=mask, keep=1, kind="bf16")
+    else:
+        S = _gram(ctx, X, y, b2.KERNEL_AUTO, mask=mask, keep=1)
+    sel = slice(None) if mask is None else (mask == 1)
+    So = orc.gram_stats(X[sel], y[sel])
+    assert S[d, d] == So[d, d]
+    assert _rel(S, So) < 2e-6
+    assert np.array_equal(S, S.T)
+    if So[d, d] > 6 * d + 10:
+        ctx.gram_import(S)
+        coef, b0 = ctx.solve()
+        fo = orc.fit_from_stats(So)
+        tol = COEF_TOL * max(1.0, 3000.0 / So[d, d]) ** 0.5 * (4 if d > 64 else 1)   # short, wide problems are ill-conditioned
+        assert np.max(np.abs(coef - fo["coef"])) < tol
+
+
 @pytest.mark.parametrize("drain", [64, 1024, 8192, 65536])
 def test_drain_interval_does_not_change_the_fit(ctx, drain):
     X, y = orc.generate_dataset(150_000, 128, seed=5, dtype=np.float32)

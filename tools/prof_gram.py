@@ -8,7 +8,9 @@ kind = sys.argv[3] if len(sys.argv) > 3 else "f32"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 ctx = b2.Context(0)
 X, y = ctx.synth(n, d, kind=kind)
-ctx.set_kernel(b2.KERNEL_TCGEN05)
+kernel = {"auto": b2.KERNEL_AUTO, "tc": b2.KERNEL_TCGEN05, "narrow": b2.KERNEL_NARROW, "simt": b2.KERNEL_SIMT}[
+    sys.argv[5] if len(sys.argv) > 5 else ("narrow" if d <= 16 else "tc")]
+ctx.set_kernel(kernel)
 for _ in range(reps):
     ctx.gram_reset(d)
     ctx.gram_accumulate(X, y)
