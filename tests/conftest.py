@@ -34,3 +34,22 @@ def ctx():
     c = b2.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def c_client(tmp_path_factory):
+    """tests/c_client/fit_client.c built with gcc against include/b2gram.h and the in-tree libb2gram.so."""
+    import shutil
+    import subprocess
+    import bodywork_mlops_demo_b200 as b2
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib_dir = os.path.dirname(b2.native.lib_path())
+    exe = str(tmp_path_factory.mktemp("c_client") / "fit_client")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O2", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_client", "fit_client.c"), "-o", exe, "-L", lib_dir, "-lb2gram", "-lm",
+           "-Wl,-rpath," + lib_dir]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    return exe

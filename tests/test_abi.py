@@ -47,6 +47,18 @@ def test_no_cpu_fallback_without_gpu():
         s1.model_metrics(np.ones(4), np.ones(4))
 
 
+def test_plain_c_client_builds_against_the_header_and_refuses_to_run_on_the_cpu(c_client):
+    """The boundary is C: a C99 translation unit with only include/b2gram.h links against the library, and without
+    a GPU the fit fails with the library's error text (exit 3) rather than falling back to host arithmetic."""
+    import subprocess
+    proc = subprocess.run([c_client], capture_output=True, text=True, timeout=120)
+    if b2.native.device_count() > 0:
+        assert proc.returncode == 0, proc.stdout + proc.stderr
+    else:
+        assert proc.returncode == 3, proc.stdout + proc.stderr
+        assert "no CPU fallback" in proc.stdout
+
+
 def test_library_has_blackwell_native_sass():
     """tcgen05 / TMA must be in the shipped binary (B200_PROFILING.md: UTC*MMA, UTMALDG, LDTM)."""
     import shutil

@@ -681,6 +681,15 @@ def test_single_bf16_operand_mode_meets_the_contract_at_large_n(ctx, kind):
     X.free(); y.free()
 
 
+def test_plain_c_client_fits_through_the_c_abi(c_client):
+    """tests/c_client/fit_client.c: C99, pageable host rows, b2_gram_accumulate(B2_MEM_HOST) + b2_solve vs a
+    double-precision normal-equation solve written out in the client."""
+    import subprocess
+    proc = subprocess.run([c_client], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "worst coefficient error" in proc.stdout
+
+
 def test_non_finite_input_is_refused_like_sklearn(ctx):
     X, y = orc.generate_dataset(5000, 8, seed=3, dtype=np.float32)
     X[17, 3] = np.nan
