@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "b2_internal.cuh"
+#include "b2_ptx.cuh"
 
 namespace b2 {
 namespace {
@@ -282,6 +283,180 @@ score_kernel_rows8(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const
   }
 }
 
+// ---- streaming path (wide contiguous rows): TMA bulk copies -> smem ring -> the same 4-rows-per-warp arithmetic -------
+// The register-fed kernel above tops out at ~0.67 of the HBM roofline: 32 warps x 4 x 16 B per lane = 64 KB in flight
+// per SM is not enough at the loaded DRAM latency (ncu r01).  Here one producer lane keeps kTmStages x 32 KB of bulk
+// copies in flight per SM (cp.async.bulk, mbarrier full/empty) and 16 consumer warps read their rows from shared
+// memory, 8 lanes per row (a 3-step xor reduce, no selects) with the per-row statistics batched 32 rows at a time.
+constexpr int kTmStages = 6;
+constexpr int kTmWarps = 15;                       // consumer warps; warp kTmWarps is the producer (16 warps: 128 registers)
+constexpr int kTmThreads = 32 * (kTmWarps + 1);
+constexpr int kTmSweepRows = kTmWarps * kRowsPerIter;          // 60 rows per sweep of the consumers
+constexpr uint32_t kTmXStage = 32768;
+constexpr int kTmMaxSweeps = 4;
+constexpr uint32_t kTmYStage = kTmSweepRows * kTmMaxSweeps * 4;   // 960 (a multiple of 16: bulk-copy granularity)
+constexpr uint32_t kTmOffY = kTmStages * kTmXStage;
+constexpr uint32_t kTmOffBar = kTmOffY + kTmStages * kTmYStage;
+constexpr uint32_t kTmSmem = kTmOffBar + 2 * kTmStages * 8 + 128;
+
+template <typename T>
+__device__ __forceinline__ void lds_row4(uint32_t addr, bool pred, float (&x)[4]);
+template <>
+__device__ __forceinline__ void lds_row4<float>(uint32_t addr, bool pred, float (&x)[4]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+      : "r"(addr), "r"((int)pred));
+}
+template <>
+__device__ __forceinline__ void lds_row4<__nv_bfloat16>(uint32_t addr, bool pred, float (&x)[4]) {
+  uint32_t u0, u1;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+      "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t"
+      "@p ld.shared.v2.b32 {%0, %1}, [%2];\n\t}"
+      : "=r"(u0), "=r"(u1)
+      : "r"(addr), "r"((int)pred));
+  x[0] = __uint_as_float(u0 << 16); x[1] = __uint_as_float(u0 & 0xffff0000u);
+  x[2] = __uint_as_float(u1 << 16); x[3] = __uint_as_float(u1 & 0xffff0000u);
+}
+
+// rows [0, n_tiles * tile_rows) of a contiguous matrix (ldx == d); tile_rows = sweeps * 60.  The row mask (1 byte per
+// row) is read straight from global memory, prefetched before the wait on the tile's barrier.
+template <typename T>
+__global__ void __launch_bounds__(kTmThreads, 1)
+score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const double* __restrict__ coef,
+                 const float* __restrict__ y, const uint8_t* __restrict__ mask, int keep, float* __restrict__ yhat,
+                 double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t bar_full = sbase + kTmOffBar, bar_empty = bar_full + 8 * kTmStages;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile_rows = sweeps * kTmSweepRows;
+  const uint32_t pitch = (uint32_t)d * sizeof(T);
+  const bool has_mask = mask != nullptr, has_y = y != nullptr;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kTmWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  __shared__ double red[kTmWarps][kNStats];
+  if (warp == kTmWarps) {
+    if (lane == 0) {
+      const uint32_t xb = (uint32_t)tile_rows * pitch, yb = (uint32_t)tile_rows * 4u;
+      const uint32_t tx = xb + (has_y ? yb : 0u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kTmStages;
+        if (it >= kTmStages) mbar_wait(bar_empty + 8 * s, (uint32_t)((it / kTmStages - 1) & 1));
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, tx);
+        const int64_t row0 = (int64_t)tile * tile_rows;
+        bulk_load_1d(sbase + s * kTmXStage, reinterpret_cast<const char*>(X) + (size_t)row0 * pitch, xb, full);
+        if (has_y) bulk_load_1d(sbase + kTmOffY + s * kTmYStage, y + row0, yb, full);
+      }
+    }
+  } else {
+    // 8 lanes per row, 4 rows per warp iteration: lane (g, j) = (lane >> 3, lane & 7) reads the 16-byte chunks
+    // j, j + 8, j + 16, j + 24 of row g (bank-conflict free), i.e. features 4 * (8 * k + j) + 0..3 for k = 0..3.
+    const int g = lane >> 3, j = lane & 7;
+    double cf[4][4];
+    bool col_ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int f0 = 4 * (8 * k + j);
+      col_ok[k] = f0 < d;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cf[k][e] = (f0 + e < d) ? coef[f0 + e] : 0.0;
+    }
+    const double b0 = coef[kMaxD];
+    const uint32_t chunk = 4u * (uint32_t)sizeof(T);            // bytes of 4 features
+    RowStats st;
+    // the statistics of a row cost ~25 fp64 instructions: lane (g, j) keeps the row of iteration j (mod 8) and all 32
+    // lanes update their statistics together once per 8 iterations
+    double p_keep = 0.0;
+    float y_keep = 0.f;
+    bool have = false;
+    int it8 = 0;
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = (int64_t)tile * tile_rows;
+      unsigned use_bits = 0xfu;
+      if (has_mask) {
+        use_bits = 0u;
+#pragma unroll
+        for (int sw = 0; sw < kTmMaxSweeps; ++sw)
+          if (sw < sweeps)
+            use_bits |= (__ldg(mask + row0 + sw * kTmSweepRows + warp * kRowsPerIter + g) == (uint8_t)keep ? 1u : 0u) << sw;
+      }
+      mbar_wait(bar_full + 8 * s, phase);
+      const uint32_t xs = sbase + s * kTmXStage, ys = sbase + kTmOffY + s * kTmYStage;
+      for (int sw = 0; sw < sweeps; ++sw) {
+        const int r = sw * kTmSweepRows + warp * kRowsPerIter + g;      // this lane group's row inside the tile
+        const bool use = (use_bits >> sw) & 1u;
+        const uint32_t row_addr = xs + (uint32_t)r * pitch + (uint32_t)j * chunk;
+        float x[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lds_row4<T>(row_addr + (uint32_t)(8 * k) * chunk, use && col_ok[k], x[k]);
+        double a0 = (double)x[0][0] * cf[0][0], a1 = (double)x[2][0] * cf[2][0];   // two chains for latency
+#pragma unroll
+        for (int e = 1; e < 4; ++e) { a0 = fma((double)x[0][e], cf[0][e], a0); a1 = fma((double)x[2][e], cf[2][e], a1); }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { a0 = fma((double)x[1][e], cf[1][e], a0); a1 = fma((double)x[3][e], cf[3][e], a1); }
+        double a = a0 + a1;
+        a += shfl_xor_d(a, 4);
+        a += shfl_xor_d(a, 2);
+        a += shfl_xor_d(a, 1);
+        const double pr = a + b0;
+        if (yhat != nullptr && j == 0) yhat[row0 + r] = use ? (float)pr : 0.f;
+        if (has_y) {
+          if (j == it8 && use) {
+            p_keep = pr;
+            y_keep = ld_shared_f32(ys + 4u * (uint32_t)r);
+            have = true;
+          }
+          if (++it8 == 8) {
+            if (have) st.add((double)y_keep, p_keep);
+            have = false;
+            it8 = 0;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      if (++s == kTmStages) { s = 0; phase ^= 1u; }
+    }
+    if (have) st.add((double)y_keep, p_keep);
+    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+#pragma unroll
+    for (int k = 0; k < kNStats; ++k) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const double other = shfl_xor_d(v[k], o);
+        v[k] = stat_is_max(k) ? fmax(v[k], other) : v[k] + other;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kNStats; ++k) red[warp][k] = v[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kNStats) {
+    const int k = threadIdx.x;
+    double acc = 0.0;
+    for (int w = 0; w < kTmWarps; ++w) acc = stat_is_max(k) ? fmax(acc, red[w][k]) : acc + red[w][k];
+    part[(size_t)blockIdx.x * kNStats + k] = acc;
+  }
+}
+
 // acc[0..5] (at part + n_ctas*6 ... see launch) = combine over CTAs in order; `first` overwrites.
 __global__ void score_reduce_kernel(const double* __restrict__ part, int n_ctas, int first, double* __restrict__ acc) {
   const int k = threadIdx.x;
@@ -292,11 +467,9 @@ __global__ void score_reduce_kernel(const double* __restrict__ part, int n_ctas,
   acc[k] = v;
 }
 
-}  // namespace
-
-// ctx->score_part layout: [score_ctas][10] partials, then 10 doubles of running totals.
-int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx, const float* y,
-                 const uint8_t* mask, int keep, float* yhat, bool first_block) {
+// register-fed kernels (any layout); `first` overwrites the running totals, otherwise they accumulate
+static int launch_score_direct(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx, const float* y,
+                               const uint8_t* mask, int keep, float* yhat, bool first) {
   const int es = x_dtype == B2_F32 ? 4 : 2;
   const int vec = (d % 4 == 0) && ((ldx * es) % (4 * es) == 0) && ((reinterpret_cast<uintptr_t>(X) % (4 * es)) == 0);
   int64_t want = (n + kScoreWarps * 4 - 1) / (kScoreWarps * 4);
@@ -320,9 +493,54 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
                                                                          ldx, ctx->coef_dev, y, mask, keep, yhat,
                                                                          vec, ctx->score_part);
   B2_CUDA(cudaGetLastError());
-  score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first_block ? 1 : 0, acc);
+  score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first ? 1 : 0, acc);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 2;
+  return B2_OK;
+}
+
+}  // namespace
+
+// ctx->score_part layout: [score_ctas][10] partials, then 10 doubles of running totals.
+int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx, const float* y,
+                 const uint8_t* mask, int keep, float* yhat, bool first_block) {
+  const int es = x_dtype == B2_F32 ? 4 : 2;
+  // wide contiguous rows stream through the TMA ring; everything else (and the < one-tile tail) is register-fed
+  const bool wide = ldx == d && d % 4 == 0 && (d * es) % 16 == 0 && d * es >= 256 &&
+                    (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  int64_t done = 0;
+  if (wide) {
+    int sweeps = (int)(kTmXStage / (uint32_t)(kTmSweepRows * d * es));
+    if (sweeps > kTmMaxSweeps) sweeps = kTmMaxSweeps;
+    const int tile_rows = sweeps * kTmSweepRows;
+    const int64_t n_tiles = n / tile_rows;
+    if (n_tiles > 0 && n_tiles <= 0x7fffffff) {
+      const int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+      double* acc = ctx->score_part + (size_t)ctx->score_ctas * kNStats;
+      if (x_dtype == B2_F32) {
+        B2_CUDA(cudaFuncSetAttribute(score_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmem));
+        score_tma_kernel<float><<<grid, kTmThreads, kTmSmem, ctx->stream>>>(
+            static_cast<const float*>(X), (int)n_tiles, sweeps, d, ctx->coef_dev, y, mask, keep, yhat, ctx->score_part);
+      } else {
+        B2_CUDA(cudaFuncSetAttribute(score_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmem));
+        score_tma_kernel<__nv_bfloat16><<<grid, kTmThreads, kTmSmem, ctx->stream>>>(
+            static_cast<const __nv_bfloat16*>(X), (int)n_tiles, sweeps, d, ctx->coef_dev, y, mask, keep, yhat,
+            ctx->score_part);
+      }
+      B2_CUDA(cudaGetLastError());
+      score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first_block ? 1 : 0, acc);
+      B2_CUDA(cudaGetLastError());
+      ctx->launches += 2;
+      done = n_tiles * tile_rows;
+      first_block = false;
+    }
+  }
+  if (done < n || n == 0) {
+    const char* Xt = static_cast<const char*>(X) + (size_t)done * ldx * es;
+    return launch_score_direct(ctx, Xt, x_dtype, n - done, d, ldx, y != nullptr ? y + done : nullptr,
+                               mask != nullptr ? mask + done : nullptr, keep, yhat != nullptr ? yhat + done : nullptr,
+                               first_block);
+  }
   return B2_OK;
 }
 

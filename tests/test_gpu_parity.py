@@ -344,6 +344,59 @@ def test_score_matches_oracle(ctx, n, d):
     assert np.max(np.abs(yh2 - p)) <= np.max(np.abs(p)) * 1e-6
 
 
+@pytest.mark.parametrize("kind", ["f32", "bf16"])
+@pytest.mark.parametrize("n,d", [(64, 128), (20_000, 128), (70_003, 64), (33_000, 96), (12_345, 100), (50_000, 72)])
+def test_streaming_score_path_matches_oracle(ctx, n, d, kind):
+    """Wide contiguous rows go through the TMA ring (full tiles) + the register-fed kernel (tail): same numbers."""
+    if kind == "bf16" and d % 8:
+        pytest.skip("bf16 rows need d % 8 == 0 for the 16-byte pitch")
+    X, y = orc.generate_dataset(n, d, seed=n + 1, dtype=np.float32)
+    if kind == "bf16":
+        bits = b2.native.to_bf16_bits(X)
+        X = b2.native.from_bf16_bits(bits)
+        Xd = ctx.to_device(bits, "bf16")
+    else:
+        Xd = ctx.to_device(X)
+    coef = np.linspace(-0.4, 0.9, d)
+    p = orc.predict(X, coef, -2.5)
+    yd = ctx.to_device(y)
+    for mask in (None, (np.arange(n) % 3 != 0).astype(np.uint8)):
+        md = ctx.to_device(mask) if mask is not None else None
+        yhat, stats = ctx.score(Xd, coef, -2.5, y=yd, row_mask=md)
+        yh = yhat.to_host()
+        sel = slice(None) if mask is None else (mask == 1)
+        assert np.max(np.abs(yh[sel] - p[sel])) <= np.max(np.abs(p)) * 1e-6
+        if mask is not None:
+            assert np.all(yh[mask == 0] == 0.0)
+        so = orc.score_stats(y[sel], p[sel])
+        assert np.max(np.abs(stats - so) / np.maximum(np.abs(so), 1e-300)) < 1e-12
+        yhat.free()
+        _, stats2 = ctx.score(Xd, coef, -2.5, y=yd, row_mask=md, want_yhat=False)      # metrics only
+        assert np.array_equal(stats, stats2)
+        yh3, none_stats = ctx.score(Xd, coef, -2.5, row_mask=md)                          # predict only
+        assert none_stats is None and np.array_equal(yh3.to_host(), yh)
+        yh3.free()
+        if md is not None:
+            md.free()
+    Xd.free(); yd.free()
+
+
+def test_streaming_score_large_batch(ctx):
+    """2 M x 128 device-resident rows (TMA ring + a 3-row register-fed tail) against the fp64 oracle."""
+    n, d = 2_000_003, 128
+    X, y = ctx.synth(n, d, seed=21)
+    coef = np.linspace(0.1, 0.9, d)
+    yh, st = ctx.score(X, coef, 0.5, y=y)
+    Xh, yh_host = X.to_host(), yh.to_host()
+    p = orc.predict(Xh[:50_000], coef, 0.5)
+    assert np.max(np.abs(yh_host[:50_000] - p)) <= np.max(np.abs(p)) * 1e-6
+    tail = slice(n - 5000, n)
+    assert np.max(np.abs(yh_host[tail] - orc.predict(Xh[tail], coef, 0.5))) <= np.max(np.abs(p)) * 1e-6
+    so = orc.score_stats(y.to_host(), orc.predict(Xh, coef, 0.5))
+    assert np.max(np.abs(st - so) / np.maximum(np.abs(so), 1e-300)) < 1e-11
+    X.free(); y.free(); yh.free()
+
+
 def test_model_metrics_matches_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_model_metrics.npz"))
     m = s1.model_metrics(g["y"], g["p"])
