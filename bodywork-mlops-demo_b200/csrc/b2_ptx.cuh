@@ -76,6 +76,80 @@ __device__ __forceinline__ float raw_ld_global<__nv_bfloat16>(const __nv_bfloat1
   return __bfloat162float(*p);
 }
 
+// ---- shared-memory row loads ---------------------------------------------------------------
+__device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds_v2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  return h;
+}
+
+// NV consecutive values of one row, vector loads (the row pitch and `addr` are multiples of the load size)
+template <typename T, int NV>
+__device__ __forceinline__ void ld_vals_vec(uint32_t addr, float (&v)[NV]) {
+  static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8 || NV == 16, "power-of-two group sizes only");
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (NV >= 4) {
+#pragma unroll
+      for (int q = 0; q < NV / 4; ++q) {
+        uint32_t r[4];
+        lds_v4(addr + 16 * q, r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[4 * q + k] = __uint_as_float(r[k]);
+      }
+    } else if constexpr (NV == 2) {
+      uint32_t r[2];
+      lds_v2(addr, r);
+      v[0] = __uint_as_float(r[0]); v[1] = __uint_as_float(r[1]);
+    } else {
+      v[0] = __uint_as_float(lds_b32(addr));
+    }
+  } else {   // bf16: two values per 32-bit word, element 0 in the low half
+    if constexpr (NV >= 8) {
+#pragma unroll
+      for (int q = 0; q < NV / 8; ++q) {
+        uint32_t r[4];
+        lds_v4(addr + 16 * q, r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[8 * q + 2 * k] = __uint_as_float(r[k] << 16);
+          v[8 * q + 2 * k + 1] = __uint_as_float(r[k] & 0xffff0000u);
+        }
+      }
+    } else if constexpr (NV == 4) {
+      uint32_t r[2];
+      lds_v2(addr, r);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { v[2 * k] = __uint_as_float(r[k] << 16); v[2 * k + 1] = __uint_as_float(r[k] & 0xffff0000u); }
+    } else if constexpr (NV == 2) {
+      const uint32_t r = lds_b32(addr);
+      v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u);
+    } else {
+      v[0] = __uint_as_float(lds_u16(addr) << 16);
+    }
+  }
+}
+
+// NV values starting at feature `start` of a row with runtime feature count d (zero beyond d)
+template <typename T, int NV>
+__device__ __forceinline__ void ld_vals_any(uint32_t row_addr, int start, int d, float (&v)[NV]) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = start + k;
+    v[k] = j < d ? raw_ld_shared<T>(row_addr + (uint32_t)j * sizeof(T)) : 0.f;
+  }
+}
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned addresses, size % 16 == 0
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(

@@ -457,6 +457,121 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
   }
 }
 
+// ---- narrow rows (D <= 16): one lane per row behind the same bulk-copy ring ---------------------------------------
+// The warp-per-row kernels above leave 31 of 32 lanes idle at the reference's own shape (one feature,
+// stage_1_train_model.py:95).  Here a lane owns a row: d conversions + d DFMAs, the statistics of 32 rows per warp
+// instruction, yhat written 128 bytes per warp.  fp64-pipe bound at D = 1 (8 bytes per row), HBM-bound from D = 4.
+constexpr int kSnStages = 6;
+constexpr int kSnWarps = 7;                        // consumer warps (+ 1 producer warp = 256 threads, 2 CTAs per SM)
+constexpr int kSnConsumers = 32 * kSnWarps;
+constexpr int kSnThreads = kSnConsumers + 32;
+
+template <int DP>
+struct SnGeom {
+  static constexpr int RPT = DP <= 2 ? 4 : (DP == 4 ? 2 : 1);   // rows per lane per stage
+  static constexpr int kRows = kSnConsumers * RPT;
+  static constexpr uint32_t kXStage = kRows * DP * 4;            // sized for fp32
+  static constexpr uint32_t kYStage = kRows * 4;
+  static constexpr uint32_t kMStage = kRows;
+  static constexpr uint32_t kOffY = kSnStages * kXStage;
+  static constexpr uint32_t kOffM = kOffY + kSnStages * kYStage;
+  static constexpr uint32_t kOffBar = kOffM + kSnStages * kMStage;
+  static constexpr uint32_t kSmem = kOffBar + 2 * kSnStages * 8 + 128;
+};
+
+template <typename T, int DP, bool EXACT>
+__global__ void __launch_bounds__(kSnThreads, 2)
+score_narrow_kernel(const T* __restrict__ X, int n_tiles, int d, const double* __restrict__ coef,
+                    const float* __restrict__ y, const uint8_t* __restrict__ mask, int keep, float* __restrict__ yhat,
+                    double* __restrict__ part) {
+  using G = SnGeom<DP>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t bar_full = sbase + G::kOffBar, bar_empty = bar_full + 8 * kSnStages;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool has_mask = mask != nullptr, has_y = y != nullptr;
+  const uint32_t row_bytes = (uint32_t)d * sizeof(T);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSnStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kSnWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  __shared__ double red[kSnWarps][kNStats];
+  if (warp == kSnWarps) {
+    if (lane == 0) {
+      const uint32_t xb = (uint32_t)G::kRows * row_bytes;
+      const uint32_t tx = xb + (has_y ? G::kYStage : 0u) + (has_mask ? G::kMStage : 0u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kSnStages;
+        if (it >= kSnStages) mbar_wait(bar_empty + 8 * s, (uint32_t)((it / kSnStages - 1) & 1));
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, tx);
+        const int64_t row0 = (int64_t)tile * G::kRows;
+        bulk_load_1d(sbase + s * G::kXStage, reinterpret_cast<const char*>(X) + (size_t)row0 * row_bytes, xb, full);
+        if (has_y) bulk_load_1d(sbase + G::kOffY + s * G::kYStage, y + row0, G::kYStage, full);
+        if (has_mask) bulk_load_1d(sbase + G::kOffM + s * G::kMStage, mask + row0, G::kMStage, full);
+      }
+    }
+  } else {
+    double cf[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) cf[k] = k < d ? coef[k] : 0.0;
+    const double b0 = coef[kMaxD];
+    RowStats st;
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(bar_full + 8 * s, phase);
+      const uint32_t xs = sbase + s * G::kXStage, ys = sbase + G::kOffY + s * G::kYStage, ms = sbase + G::kOffM + s * G::kMStage;
+      const int64_t row0 = (int64_t)tile * G::kRows;
+#pragma unroll
+      for (int rr = 0; rr < G::RPT; ++rr) {
+        const int r = rr * kSnConsumers + threadIdx.x;          // consecutive lanes, consecutive rows
+        const bool use = !has_mask || ld_shared_u8(ms + (uint32_t)r) == (uint32_t)keep;
+        float x[DP];
+        if constexpr (EXACT) ld_vals_vec<T, DP>(xs + (uint32_t)r * row_bytes, x);
+        else ld_vals_any<T, DP>(xs + (uint32_t)r * row_bytes, 0, d, x);
+        double a0 = b0, a1 = 0.0;                                // two chains
+#pragma unroll
+        for (int k = 0; k < DP; k += 2) {
+          a0 = fma((double)x[k], cf[k], a0);
+          if (k + 1 < DP) a1 = fma((double)x[k + 1], cf[k + 1], a1);
+        }
+        const double pr = a0 + a1;
+        if (yhat != nullptr) yhat[row0 + r] = use ? (float)pr : 0.f;
+        if (has_y && use) st.add((double)ld_shared_f32(ys + 4u * (uint32_t)r), pr);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      if (++s == kSnStages) { s = 0; phase ^= 1u; }
+    }
+    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+#pragma unroll
+    for (int k = 0; k < kNStats; ++k) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const double other = shfl_xor_d(v[k], o);
+        v[k] = stat_is_max(k) ? fmax(v[k], other) : v[k] + other;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < kNStats; ++k) red[warp][k] = v[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kNStats) {
+    const int k = threadIdx.x;
+    double acc = 0.0;
+    for (int w = 0; w < kSnWarps; ++w) acc = stat_is_max(k) ? fmax(acc, red[w][k]) : acc + red[w][k];
+    part[(size_t)blockIdx.x * kNStats + k] = acc;
+  }
+}
+
 // acc[0..5] (at part + n_ctas*6 ... see launch) = combine over CTAs in order; `first` overwrites.
 __global__ void score_reduce_kernel(const double* __restrict__ part, int n_ctas, int first, double* __restrict__ acc) {
   const int k = threadIdx.x;
@@ -499,6 +614,43 @@ static int launch_score_direct(b2_ctx* ctx, const void* X, int x_dtype, int64_t 
   return B2_OK;
 }
 
+template <typename T, int DP>
+static int launch_score_narrow_dp(b2_ctx* ctx, const T* X, int64_t n, int d, const float* y, const uint8_t* mask, int keep,
+                                  float* yhat, bool first, int64_t* done) {
+  using G = SnGeom<DP>;
+  const int64_t n_tiles = n / G::kRows;
+  *done = 0;
+  if (n_tiles == 0 || n_tiles > 0x7fffffff) return B2_OK;
+  const int cap = ctx->sm_count * 2;
+  const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+  if (d == DP) {
+    B2_CUDA(cudaFuncSetAttribute(score_narrow_kernel<T, DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
+    score_narrow_kernel<T, DP, true><<<grid, kSnThreads, G::kSmem, ctx->stream>>>(X, (int)n_tiles, d, ctx->coef_dev, y, mask,
+                                                                                  keep, yhat, ctx->score_part);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(score_narrow_kernel<T, DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
+    score_narrow_kernel<T, DP, false><<<grid, kSnThreads, G::kSmem, ctx->stream>>>(X, (int)n_tiles, d, ctx->coef_dev, y, mask,
+                                                                                   keep, yhat, ctx->score_part);
+  }
+  B2_CUDA(cudaGetLastError());
+  score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first ? 1 : 0,
+                                                 ctx->score_part + (size_t)ctx->score_ctas * kNStats);
+  B2_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+  *done = n_tiles * G::kRows;
+  return B2_OK;
+}
+
+template <typename T>
+static int launch_score_narrow(b2_ctx* ctx, const T* X, int64_t n, int d, const float* y, const uint8_t* mask, int keep,
+                               float* yhat, bool first, int64_t* done) {
+  if (d <= 1) return launch_score_narrow_dp<T, 1>(ctx, X, n, d, y, mask, keep, yhat, first, done);
+  if (d <= 2) return launch_score_narrow_dp<T, 2>(ctx, X, n, d, y, mask, keep, yhat, first, done);
+  if (d <= 4) return launch_score_narrow_dp<T, 4>(ctx, X, n, d, y, mask, keep, yhat, first, done);
+  if (d <= 8) return launch_score_narrow_dp<T, 8>(ctx, X, n, d, y, mask, keep, yhat, first, done);
+  return launch_score_narrow_dp<T, 16>(ctx, X, n, d, y, mask, keep, yhat, first, done);
+}
+
 }  // namespace
 
 // ctx->score_part layout: [score_ctas][10] partials, then 10 doubles of running totals.
@@ -508,8 +660,20 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
   // wide contiguous rows stream through the TMA ring; everything else (and the < one-tile tail) is register-fed
   const bool wide = ldx == d && d % 4 == 0 && (d * es) % 16 == 0 && d * es >= 256 &&
                     (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  const bool narrow = ldx == d && d <= 16 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                      (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                      (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
   int64_t done = 0;
-  if (wide) {
+  if (narrow) {
+    int rc;
+    if (x_dtype == B2_F32)
+      rc = launch_score_narrow<float>(ctx, static_cast<const float*>(X), n, d, y, mask, keep, yhat, first_block, &done);
+    else
+      rc = launch_score_narrow<__nv_bfloat16>(ctx, static_cast<const __nv_bfloat16*>(X), n, d, y, mask, keep, yhat,
+                                              first_block, &done);
+    if (rc != B2_OK) return rc;
+    if (done > 0) first_block = false;
+  } else if (wide) {
     int sweeps = (int)(kTmXStage / (uint32_t)(kTmSweepRows * d * es));
     if (sweeps > kTmMaxSweeps) sweeps = kTmMaxSweeps;
     const int tile_rows = sweeps * kTmSweepRows;

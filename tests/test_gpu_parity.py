@@ -381,6 +381,54 @@ def test_streaming_score_path_matches_oracle(ctx, n, d, kind):
     Xd.free(); yd.free()
 
 
+@pytest.mark.parametrize("kind", ["f32", "bf16"])
+@pytest.mark.parametrize("n,d", [(5000, 1), (33_333, 1), (20_000, 2), (9_001, 3), (12_000, 4), (7_000, 5), (30_001, 8),
+                                 (5_000, 12), (11_111, 16)])
+def test_narrow_score_path_matches_oracle(ctx, n, d, kind):
+    """D <= 16: one lane per row behind the bulk-copy ring (full tiles) + the register-fed kernel (tail)."""
+    X, y = orc.generate_dataset(n, d, seed=n + 7, dtype=np.float32)
+    if kind == "bf16":
+        bits = b2.native.to_bf16_bits(X)
+        X = b2.native.from_bf16_bits(bits)
+        Xd = ctx.to_device(bits, "bf16")
+    else:
+        Xd = ctx.to_device(X)
+    coef = np.linspace(0.45, 0.6, d)
+    p = orc.predict(X, coef, 0.75)
+    yd = ctx.to_device(y)
+    for mask in (None, s1.split_mask(n)):
+        md = ctx.to_device(mask) if mask is not None else None
+        for keep in ((1,) if mask is None else (0, 1)):
+            yhat, stats = ctx.score(Xd, coef, 0.75, y=yd, row_mask=md, mask_keep=keep)
+            yh = yhat.to_host()
+            sel = slice(None) if mask is None else (mask == keep)
+            assert np.max(np.abs(yh[sel] - p[sel])) <= np.max(np.abs(p)) * 1e-6
+            if mask is not None:
+                assert np.all(yh[mask != keep] == 0.0)
+            so = orc.score_stats(y[sel], p[sel])
+            assert np.max(np.abs(stats - so) / np.maximum(np.abs(so), 1e-300)) < 1e-12
+            yhat.free()
+        if md is not None:
+            md.free()
+    Xd.free(); yd.free()
+
+
+def test_reference_shape_train_model_at_scale(ctx):
+    """The reference's own shape (one feature) at 50 M rows: masked fit (narrow Gram) + hold-out metrics (narrow score)
+    recover the generator's truth, and the two passes see complementary row sets."""
+    n = 50_000_000 + 123
+    X, y = ctx.synth(n, 1, seed=2024)
+    mask = ctx.to_device((np.arange(n, dtype=np.int64) % 5 != 0).astype(np.uint8))     # 80 / 20 like stage_1...:98-103
+    est = b2.B200LinearRegression(ctx=ctx)
+    est.fit(X, y, row_mask=mask, mask_keep=1, with_spectrum=False)
+    assert abs(est.coef_[0] - 0.5) < 2e-4 and abs(est.intercept_ - 1.0) < 2e-2
+    _, stats = ctx.score(X, est.coef_, float(est.intercept_), y=y, row_mask=mask, mask_keep=0, want_yhat=False)
+    assert stats[5] == n - int(round(ctx.gram_export()[1, 1]))              # hold-out rows = all rows - training rows
+    mape, r2, mx = s1.metrics_from_stats(stats)
+    assert 0.65 < r2 < 0.70                 # var(0.5 x) / (var(0.5 x) + 100) = 208.3 / 308.3
+    X.free(); y.free(); mask.free()
+
+
 def test_streaming_score_large_batch(ctx):
     """2 M x 128 device-resident rows (TMA ring + a 3-row register-fed tail) against the fp64 oracle."""
     n, d = 2_000_003, 128
