@@ -291,10 +291,10 @@ score_kernel_rows8(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const
 constexpr int kTmStages = 6;
 constexpr int kTmWarps = 15;                       // consumer warps; warp kTmWarps is the producer (16 warps: 128 registers)
 constexpr int kTmThreads = 32 * (kTmWarps + 1);
-constexpr int kTmSweepRows = kTmWarps * kRowsPerIter;          // 60 rows per sweep of the consumers
+constexpr int kTmTileRowsMax = 240;                // rows per stage (y tile: 960 B)
 constexpr uint32_t kTmXStage = 32768;
 constexpr int kTmMaxSweeps = 4;
-constexpr uint32_t kTmYStage = kTmSweepRows * kTmMaxSweeps * 4;   // 960 (a multiple of 16: bulk-copy granularity)
+constexpr uint32_t kTmYStage = kTmTileRowsMax * 4;                // 960 (a multiple of 16: bulk-copy granularity)
 constexpr uint32_t kTmOffY = kTmStages * kTmXStage;
 constexpr uint32_t kTmOffBar = kTmOffY + kTmStages * kTmYStage;
 constexpr uint32_t kTmSmem = kTmOffBar + 2 * kTmStages * 8 + 128;
@@ -323,9 +323,10 @@ __device__ __forceinline__ void lds_row4<__nv_bfloat16>(uint32_t addr, bool pred
   x[2] = __uint_as_float(u1 << 16); x[3] = __uint_as_float(u1 & 0xffff0000u);
 }
 
-// rows [0, n_tiles * tile_rows) of a contiguous matrix (ldx == d); tile_rows = sweeps * 60.  The row mask (1 byte per
-// row) is read straight from global memory, prefetched before the wait on the tile's barrier.
-template <typename T>
+// rows [0, n_tiles * tile_rows) of a contiguous matrix (ldx == d).  LPR lanes share a row (8: up to 128 features,
+// 4: up to 64, 2: up to 32), 32 / LPR rows per warp iteration, tile_rows = sweeps * 15 * 32 / LPR.  The row mask
+// (1 byte per row) is read straight from global memory, prefetched before the wait on the tile's barrier.
+template <typename T, int LPR>
 __global__ void __launch_bounds__(kTmThreads, 1)
 score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const double* __restrict__ coef,
                  const float* __restrict__ y, const uint8_t* __restrict__ mask, int keep, float* __restrict__ yhat,
@@ -334,7 +335,8 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t bar_full = sbase + kTmOffBar, bar_empty = bar_full + 8 * kTmStages;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile_rows = sweeps * kTmSweepRows;
+  constexpr int RPI = 32 / LPR, kSweepRows = kTmWarps * RPI;
+  const int tile_rows = sweeps * kSweepRows;
   const uint32_t pitch = (uint32_t)d * sizeof(T);
   const bool has_mask = mask != nullptr, has_y = y != nullptr;
   if (threadIdx.x == 0) {
@@ -363,23 +365,26 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
       }
     }
   } else {
-    // 8 lanes per row, 4 rows per warp iteration: lane (g, j) = (lane >> 3, lane & 7) reads the 16-byte chunks
-    // j, j + 8, j + 16, j + 24 of row g (bank-conflict free), i.e. features 4 * (8 * k + j) + 0..3 for k = 0..3.
-    const int g = lane >> 3, j = lane & 7;
+    // LPR lanes per row, RPI rows per warp iteration: lane (g, j) = (lane / LPR, lane % LPR) reads the 4-feature chunks
+    // kk * LPR + j of row g, kk = (k + g) mod 4 for k = 0..3 -- the rotation by g keeps the rows of one shared-memory
+    // wavefront on different banks when the row pitch is 128 or 256 bytes.
+    const int g = lane / LPR, j = lane % LPR;
     double cf[4][4];
     bool col_ok[4];
+    uint32_t coff[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int f0 = 4 * (8 * k + j);
+      const int c = ((k + g) & 3) * LPR + j;
+      const int f0 = 4 * c;
       col_ok[k] = f0 < d;
+      coff[k] = (uint32_t)c * 4u * (uint32_t)sizeof(T);
 #pragma unroll
       for (int e = 0; e < 4; ++e) cf[k][e] = (f0 + e < d) ? coef[f0 + e] : 0.0;
     }
     const double b0 = coef[kMaxD];
-    const uint32_t chunk = 4u * (uint32_t)sizeof(T);            // bytes of 4 features
     RowStats st;
-    // the statistics of a row cost ~25 fp64 instructions: lane (g, j) keeps the row of iteration j (mod 8) and all 32
-    // lanes update their statistics together once per 8 iterations
+    // the statistics of a row cost ~25 fp64 instructions: lane (g, j) keeps the row of iteration j (mod LPR) and all 32
+    // lanes update their statistics together once per LPR iterations
     double p_keep = 0.0;
     float y_keep = 0.f;
     bool have = false;
@@ -394,26 +399,25 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
 #pragma unroll
         for (int sw = 0; sw < kTmMaxSweeps; ++sw)
           if (sw < sweeps)
-            use_bits |= (__ldg(mask + row0 + sw * kTmSweepRows + warp * kRowsPerIter + g) == (uint8_t)keep ? 1u : 0u) << sw;
+            use_bits |= (__ldg(mask + row0 + sw * kSweepRows + warp * RPI + g) == (uint8_t)keep ? 1u : 0u) << sw;
       }
       mbar_wait(bar_full + 8 * s, phase);
       const uint32_t xs = sbase + s * kTmXStage, ys = sbase + kTmOffY + s * kTmYStage;
       for (int sw = 0; sw < sweeps; ++sw) {
-        const int r = sw * kTmSweepRows + warp * kRowsPerIter + g;      // this lane group's row inside the tile
+        const int r = sw * kSweepRows + warp * RPI + g;                 // this lane group's row inside the tile
         const bool use = (use_bits >> sw) & 1u;
-        const uint32_t row_addr = xs + (uint32_t)r * pitch + (uint32_t)j * chunk;
+        const uint32_t row_addr = xs + (uint32_t)r * pitch;
         float x[4][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lds_row4<T>(row_addr + (uint32_t)(8 * k) * chunk, use && col_ok[k], x[k]);
+        for (int k = 0; k < 4; ++k) lds_row4<T>(row_addr + coff[k], use && col_ok[k], x[k]);
         double a0 = (double)x[0][0] * cf[0][0], a1 = (double)x[2][0] * cf[2][0];   // two chains for latency
 #pragma unroll
         for (int e = 1; e < 4; ++e) { a0 = fma((double)x[0][e], cf[0][e], a0); a1 = fma((double)x[2][e], cf[2][e], a1); }
 #pragma unroll
         for (int e = 0; e < 4; ++e) { a0 = fma((double)x[1][e], cf[1][e], a0); a1 = fma((double)x[3][e], cf[3][e], a1); }
         double a = a0 + a1;
-        a += shfl_xor_d(a, 4);
-        a += shfl_xor_d(a, 2);
-        a += shfl_xor_d(a, 1);
+#pragma unroll
+        for (int o = LPR / 2; o >= 1; o >>= 1) a += shfl_xor_d(a, o);
         const double pr = a + b0;
         if (yhat != nullptr && j == 0) yhat[row0 + r] = use ? (float)pr : 0.f;
         if (has_y) {
@@ -422,7 +426,7 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
             y_keep = ld_shared_f32(ys + 4u * (uint32_t)r);
             have = true;
           }
-          if (++it8 == 8) {
+          if (++it8 == LPR) {
             if (have) st.add((double)y_keep, p_keep);
             have = false;
             it8 = 0;
@@ -658,8 +662,8 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
                  const uint8_t* mask, int keep, float* yhat, bool first_block) {
   const int es = x_dtype == B2_F32 ? 4 : 2;
   // wide contiguous rows stream through the TMA ring; everything else (and the < one-tile tail) is register-fed
-  const bool wide = ldx == d && d % 4 == 0 && (d * es) % 16 == 0 && d * es >= 256 &&
-                    (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  const bool wide = ldx == d && d > 16 && d % 4 == 0 && (d * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                    (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const bool narrow = ldx == d && d <= 16 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
                       (y == nullptr || (reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                       (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
@@ -674,23 +678,27 @@ int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int6
     if (rc != B2_OK) return rc;
     if (done > 0) first_block = false;
   } else if (wide) {
-    int sweeps = (int)(kTmXStage / (uint32_t)(kTmSweepRows * d * es));
-    if (sweeps > kTmMaxSweeps) sweeps = kTmMaxSweeps;
-    const int tile_rows = sweeps * kTmSweepRows;
+    const int lpr = d <= 32 ? 2 : (d <= 64 ? 4 : 8);             // lanes per row: 4 chunks of 4 features per lane
+    const int sweep_rows = kTmWarps * (32 / lpr);
+    int sweeps = (int)(kTmXStage / (uint32_t)(sweep_rows * d * es));
+    if (sweeps > kTmTileRowsMax / sweep_rows) sweeps = kTmTileRowsMax / sweep_rows;
+    const int tile_rows = sweeps * sweep_rows;
     const int64_t n_tiles = n / tile_rows;
     if (n_tiles > 0 && n_tiles <= 0x7fffffff) {
       const int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
       double* acc = ctx->score_part + (size_t)ctx->score_ctas * kNStats;
-      if (x_dtype == B2_F32) {
-        B2_CUDA(cudaFuncSetAttribute(score_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmem));
-        score_tma_kernel<float><<<grid, kTmThreads, kTmSmem, ctx->stream>>>(
-            static_cast<const float*>(X), (int)n_tiles, sweeps, d, ctx->coef_dev, y, mask, keep, yhat, ctx->score_part);
-      } else {
-        B2_CUDA(cudaFuncSetAttribute(score_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmem));
-        score_tma_kernel<__nv_bfloat16><<<grid, kTmThreads, kTmSmem, ctx->stream>>>(
-            static_cast<const __nv_bfloat16*>(X), (int)n_tiles, sweeps, d, ctx->coef_dev, y, mask, keep, yhat,
-            ctx->score_part);
-      }
+#define B2_LAUNCH_TM(T, LPR)                                                                                          \
+  do {                                                                                                                \
+    B2_CUDA(cudaFuncSetAttribute(score_tma_kernel<T, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmSmem));    \
+    score_tma_kernel<T, LPR><<<grid, kTmThreads, kTmSmem, ctx->stream>>>(static_cast<const T*>(X), (int)n_tiles, sweeps, \
+                                                                         d, ctx->coef_dev, y, mask, keep, yhat,       \
+                                                                         ctx->score_part);                            \
+  } while (0)
+#define B2_LAUNCH_TM_T(T) \
+  do { if (lpr == 2) B2_LAUNCH_TM(T, 2); else if (lpr == 4) B2_LAUNCH_TM(T, 4); else B2_LAUNCH_TM(T, 8); } while (0)
+      if (x_dtype == B2_F32) B2_LAUNCH_TM_T(float); else B2_LAUNCH_TM_T(__nv_bfloat16);
+#undef B2_LAUNCH_TM_T
+#undef B2_LAUNCH_TM
       B2_CUDA(cudaGetLastError());
       score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first_block ? 1 : 0, acc);
       B2_CUDA(cudaGetLastError());

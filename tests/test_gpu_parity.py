@@ -345,7 +345,8 @@ def test_score_matches_oracle(ctx, n, d):
 
 
 @pytest.mark.parametrize("kind", ["f32", "bf16"])
-@pytest.mark.parametrize("n,d", [(64, 128), (20_000, 128), (70_003, 64), (33_000, 96), (12_345, 100), (50_000, 72)])
+@pytest.mark.parametrize("n,d", [(64, 128), (20_000, 128), (70_003, 64), (33_000, 96), (12_345, 100), (50_000, 72),
+                                 (40_000, 32), (25_003, 20), (30_000, 48), (9_000, 24), (15_000, 40)])
 def test_streaming_score_path_matches_oracle(ctx, n, d, kind):
     """Wide contiguous rows go through the TMA ring (full tiles) + the register-fed kernel (tail): same numbers."""
     if kind == "bf16" and d % 8:
