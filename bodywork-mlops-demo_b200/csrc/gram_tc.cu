@@ -58,9 +58,11 @@ constexpr uint32_t kTmemALoCol = 432;                         // TS: A = lo oper
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffOp = kOffRaw + kRawStages * kRawStageBytes;     // 131072
 constexpr uint32_t kOffY = kOffOp + kOpStages * kOpStageBytes;         // 200704
-constexpr int kMaxPack = 4;                                             // original rows per 128-wide super-row
-constexpr uint32_t kYStageBytes = kTcRows * kMaxPack * 4;               // 1024
-constexpr uint32_t kMStageBytes = kTcRows * kMaxPack;                   // 256
+constexpr int kMaxPack = 5;                                             // original rows per 128-wide super-row (3 E columns each)
+constexpr uint32_t kYStageBytes = kTcRows * kMaxPack * 4;               // 1280
+constexpr uint32_t kMStageBytes = 384;                                  // 64 * kMaxPack = 320 mask bytes, padded: TMA
+                                                                        // destinations are 128-byte aligned
+static_assert(kMStageBytes >= kTcRows * kMaxPack && kMStageBytes % 128 == 0 && kYStageBytes % 128 == 0, "stage alignment");
 constexpr uint32_t kOffMask = kOffY + kRawStages * kYStageBytes;
 constexpr uint32_t kOffBar = kOffMask + kRawStages * kMStageBytes;
 constexpr int kNumBars = 2 * kRawStages + 2 * kOpStages + 4;
@@ -208,7 +210,8 @@ template <typename T, int DFIX, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
-               int64_t n_rows, int d_arg, int pack, int64_t n_shift, const float* __restrict__ shift, int chunk_tiles,
+               int64_t n_rows, int d_arg, int pack, int d_orig, int64_t n_shift, const float* __restrict__ shift,
+               int chunk_tiles,
                double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg) {
 #ifdef B2_DEV_KNOBS
   const uint32_t dbg = dbg_arg;      // ablation switches (tools/build_dev.sh): results are WRONG when non-zero
@@ -270,10 +273,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // zero the operand stages once: feature rows >= d, the unused E rows and the lo/hi padding read as 0
   for (uint32_t o = threadIdx.x * 16; o < kOpStages * kOpStageBytes; o += kThreads * 16)
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
-  // packed rows (pack > 1): super-row feature i is original feature i % (128 / pack) -> the shift repeats
-  const int d_orig = d / pack;
+  // packed rows (pack > 1): super-row feature i < pack * d_orig is original feature i % d_orig -> the shift repeats;
+  // the columns from pack * d_orig to 127 are TMA out-of-bounds zero fill and keep shift 0 (they contribute nothing)
   for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
-    shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift) : (j < d ? shift_value(shift, j % d_orig, n_shift) : 0.f);
+    shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift)
+                              : (j < pack * d_orig ? shift_value(shift, j % d_orig, n_shift) : 0.f);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -296,7 +300,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int sub0 = (int)row0 * pack;                               // first original row of the tile
         if (y_map_2d) tma_load_2d(sbase + kOffY + s * kYStageBytes, &tmY, 0, sub0 >> 2, full);
         else tma_load_1d(sbase + kOffY + s * kYStageBytes, &tmY, sub0, full);
-        if (has_mask) tma_load_1d(sbase + kOffMask + s * kMStageBytes, &tmM, sub0, full);
+        if (has_mask == 2) tma_load_2d(sbase + kOffMask + s * kMStageBytes, &tmM, 0, sub0 >> 4, full);
+        else if (has_mask) tma_load_1d(sbase + kOffMask + s * kMStageBytes, &tmM, sub0, full);
         if (++s == kRawStages) { s = 0; ph ^= 1; }
       }
     }
@@ -666,23 +671,24 @@ bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, in
   return true;
 }
 
+// d: inner extent of the (super-)row tensor; d_box: inner extent of the smem tile (> d: the rest is zero fill)
 static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int es, const float* y, int64_t n, int d,
-                       int64_t ldx, int64_t n_y, int pack, const uint8_t* mask, CUtensorMap* tmX_out,
-                       CUtensorMap* tmY_out, CUtensorMap* tmM_out, int* y_map_2d_out) {
+                       int d_box, int64_t ldx, int64_t n_y, int pack, const uint8_t* mask, CUtensorMap* tmX_out,
+                       CUtensorMap* tmY_out, CUtensorMap* tmM_out, int* y_map_2d_out, int* m_map_2d_out) {
   const cuuint32_t y_box = (cuuint32_t)(kTcRows * pack);   // original rows per tile
   CUtensorMap& tmX = *tmX_out; CUtensorMap& tmY = *tmY_out; CUtensorMap& tmM = *tmM_out;
   memset(&tmM, 0, sizeof(tmM));
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)ldx * es};
-    cuuint32_t box[2] = {(cuuint32_t)d, (cuuint32_t)kTcRows};
+    cuuint32_t box[2] = {(cuuint32_t)d_box, (cuuint32_t)kTcRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmX, x_dtype == B2_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                         2, const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(X) failed with %d (n=%lld d=%d ldx=%lld)", (int)r, (long long)n, d,
+      set_error("cuTensorMapEncodeTiled(X) failed with %d (n=%lld d=%d box=%d ldx=%lld)", (int)r, (long long)n, d, d_box,
                 (long long)ldx);
       return B2_E_CUDA;
     }
@@ -693,9 +699,11 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
     cuuint64_t strides[1] = {0};
     cuuint32_t box[1] = {y_box};
     cuuint32_t estr[1] = {1};
-    CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(y), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = CUDA_ERROR_INVALID_VALUE;
+    if (y_box <= 256)
+      r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(y), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       // rank-1 maps refused: view y as [ceil(n/4)][4] (16-byte rows) -- the same bytes land in smem
       cuuint64_t dims2[2] = {4, (cuuint64_t)((n_y + 3) / 4)};
@@ -716,20 +724,35 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
     set_error("row_mask must be 16-byte aligned for the tcgen05 path");
     return B2_E_ARG;
   }
+  int m_map_2d = 0;
   if (mask != nullptr) {
     cuuint64_t dims[1] = {(cuuint64_t)n_y};
     cuuint64_t strides[1] = {0};
     cuuint32_t box[1] = {y_box};
     cuuint32_t estr[1] = {1};
-    CUresult r = encode(&tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, const_cast<uint8_t*>(mask), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = CUDA_ERROR_INVALID_VALUE;
+    if (y_box <= 256)
+      r = encode(&tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, const_cast<uint8_t*>(mask), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && n_y % 16 == 0) {
+      // box extents stop at 256: view the mask as [n/16][16] (16-byte rows) -- the same bytes land in smem
+      cuuint64_t dims2[2] = {16, (cuuint64_t)(n_y / 16)};
+      cuuint64_t strides2[1] = {16};
+      cuuint32_t box2[2] = {16, y_box / 16};
+      cuuint32_t estr2[2] = {1, 1};
+      r = encode(&tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(mask), dims2, strides2, box2, estr2,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      m_map_2d = 1;
+    }
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(mask) failed with %d", (int)r);
       return B2_E_CUDA;
     }
   }
 
+  *m_map_2d_out = m_map_2d;
   *y_map_2d_out = y_map_2d;
   return B2_OK;
 }
@@ -742,28 +765,38 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     return B2_E_CUDA;
   }
   const int es = x_dtype == B2_F32 ? 4 : 2;
-  // Row packing: contiguous rows of 32 / 64 features are viewed as [n / pack][128] super-rows and run on the
-  // D = 128 fast path; the diagonal blocks of the 128 x 128 Gram sum to the true statistic (tc_fold_kernel).
-  // The n % pack leftover rows (at most 3) go through the CUDA-core kernel.
+  // Row packing: `pack` contiguous rows of 17..64 features are viewed as one super-row of pack * d_in <= 128 columns
+  // ([n / pack][pack * d_in], zero-filled by TMA to the 128-wide tile) and run on the D = 128 fast path; the diagonal
+  // d_in x d_in blocks of the 128 x 128 Gram sum to the true statistic (tc_fold_kernel).  The tensor maps cover a
+  // multiple of lcm(pack, 16) rows (the y / mask views are 16-byte rows); the < 80 leftover rows go through the
+  // CUDA-core kernel.
   int pack = 1;
-  if ((d_in == 32 || d_in == 64) && ldx_in == d_in && n_in >= (int64_t)kTcRows * (128 / d_in)) pack = 128 / d_in;
-  const int64_t n_main = n_in - n_in % pack;           // original rows handled here
+  if (d_in > 16 && d_in <= 64 && ldx_in == d_in) {
+    pack = 128 / d_in;
+    if (pack > kMaxPack) pack = kMaxPack;
+    if (n_in < (int64_t)2 * kTcRows * pack) pack = 1;
+  }
+  const int group = pack == 1 ? 1 : (pack == 3 ? 48 : (pack == 5 ? 80 : 16));
+  const int64_t n_main = n_in - n_in % group;          // original rows handled here
   const int64_t n = n_main / pack;                      // super-rows
-  const int d = d_in * pack;
+  const int d = pack > 1 ? 128 : d_in;                  // kernel feature count (DFIX = 128 when packed)
+  const int d_tensor = d_in * pack;                     // columns that exist; the tile is zero-filled beyond them
   const int64_t ldx = ldx_in * pack;
   const int64_t n_y = n_main;                           // y / mask elements covered by the tensor maps
   CUtensorMap tmX, tmY, tmM;
-  int y_map_2d = 0;
+  int y_map_2d = 0, m_map_2d = 0;
   b2_ctx::TmCache& tc = ctx->tm_cache;
   const bool cached = tc.X == X && tc.y == y && tc.mask == mask && tc.n == n_in && tc.ldx == ldx_in && tc.d == d_in &&
                       tc.x_dtype == x_dtype;
   if (cached) {
     memcpy(&tmX, tc.tmX, sizeof(tmX)); memcpy(&tmY, tc.tmY, sizeof(tmY)); memcpy(&tmM, tc.tmM, sizeof(tmM));
-    y_map_2d = tc.y_map_2d;
+    y_map_2d = tc.y_map_2d & 1; m_map_2d = (tc.y_map_2d >> 1) & 1;
   } else {
-    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d, ldx, n_y, pack, mask, &tmX, &tmY, &tmM, &y_map_2d)) return r;
+    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d_tensor, d, ldx, n_y, pack, mask, &tmX, &tmY, &tmM, &y_map_2d,
+                            &m_map_2d))
+      return r;
     tc.X = X; tc.y = y; tc.mask = mask; tc.n = n_in; tc.ldx = ldx_in; tc.d = d_in; tc.x_dtype = x_dtype;
-    tc.y_map_2d = y_map_2d;
+    tc.y_map_2d = y_map_2d | (m_map_2d << 1);
     memcpy(tc.tmX, &tmX, sizeof(tmX)); memcpy(tc.tmY, &tmY, sizeof(tmY)); memcpy(tc.tmM, &tmM, sizeof(tmM));
   }
 
@@ -811,7 +844,8 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
 #define B2_LAUNCH_TC(T, DF, SP)                                                                          \
   gram_tc_kernel<T, DF, SP><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                \
-      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 : 0, keep, n, d, pack, n_in, ctx->shift, chunk_tiles,  \
+      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 + m_map_2d : 0, keep, n, d, pack, d_in, n_in, ctx->shift, \
+      chunk_tiles,                                                                                        \
       ctx->tc_part, ctx->tc_side, wait_ns, dbg)
 #define B2_LAUNCH_TC_D(T, SP) \
   do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)

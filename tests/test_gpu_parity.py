@@ -56,7 +56,10 @@ def test_simt_gram_matches_oracle(ctx, n, d):
 
 
 @pytest.mark.parametrize("n,d", [(64, 128), (4096, 128), (100_003, 128), (50_000, 32), (20_001, 8), (65_536, 64),
-                                 (9_999, 4), (40_000, 100)])
+                                 (9_999, 4), (40_000, 100),
+                                 # packed super-rows with a zero-filled tail: pack = 5, 5, 4, 3, 3, 2, 2
+                                 (30_011, 20), (25_000, 24), (40_003, 28), (20_000, 36), (33_333, 40), (45_001, 48),
+                                 (10_000, 60)])
 def test_tcgen05_gram_matches_oracle(ctx, n, d):
     X, y = orc.generate_dataset(n, d, seed=n + d, dtype=np.float32)
     S = _gram(ctx, X, y, b2.KERNEL_TCGEN05)
@@ -221,6 +224,30 @@ def test_row_mask_equals_gather(ctx, kernel):
     So = orc.gram_stats(X[mask == 1], y[mask == 1])
     assert S[64, 64] == int((mask == 1).sum())
     assert _rel(S, So) < (1e-12 if kernel == b2.KERNEL_SIMT else 2e-6)
+
+
+@pytest.mark.parametrize("d,kind", [(20, "f32"), (24, "f32"), (40, "f32"), (48, "f32"), (24, "bf16"), (40, "bf16"),
+                                    (56, "bf16")])
+def test_packed_rows_with_mask_and_bf16(ctx, d, kind):
+    """pack * d < 128: the tile tail is TMA zero fill; the row mask is per original row (2-D mask view at pack = 5)."""
+    X, y = orc.generate_dataset(52_345, d, seed=d, dtype=np.float32)
+    mask = s1.split_mask(X.shape[0])
+    if kind == "bf16":
+        bits = b2.native.to_bf16_bits(X)
+        X = b2.native.from_bf16_bits(bits)
+        src = bits
+    else:
+        src = X
+    for keep in (1, 0):
+        S = _gram(ctx, src, y, b2.KERNEL_TCGEN05, mask=mask, keep=keep, kind=kind if kind == "bf16" else None)
+        So = orc.gram_stats(X[mask == keep], y[mask == keep])
+        assert S[d, d] == int((mask == keep).sum())
+        assert _rel(S, So) < 2e-6
+    S = _gram(ctx, src, y, b2.KERNEL_AUTO, kind=kind if kind == "bf16" else None)     # AUTO takes the same path
+    assert _rel(S, orc.gram_stats(X, y)) < 2e-6
+    ctx.gram_import(S)
+    coef, _ = ctx.solve()
+    assert np.max(np.abs(coef - orc.fit_from_stats(orc.gram_stats(X, y))["coef"])) < COEF_TOL
 
 
 def test_bf16_storage_fits_the_bf16_rows(ctx):
