@@ -374,6 +374,23 @@ def main() -> None:
             if vk != kind:
                 Xv.free(); yv.free()
 
+    # ---- companion kernel: hold-out scoring + metrics over the same resident rows (stage_1...:107, 79-90) ----------
+    companion = None
+    if world == 1 and not args.no_variants:
+        ctx.set_kernel(b2.KERNEL_AUTO)
+        for _ in range(3):
+            ctx.score(X, coef, float(b0), y=y, want_yhat=False)
+        ctx.sync(); ctx.timer_start()
+        for _ in range(10):
+            _yh, sstats = ctx.score(X, coef, float(b0), y=y, want_yhat=False)
+        sms = ctx.timer_stop() / 10
+        sbpr = D * (4 if kind == "f32" else 2) + 4
+        companion = {"what": "b2_score: X.coef + intercept fused with the ten metric reductions, resident rows, no yhat write",
+                     "ms": sms, "rows_per_s": rows / sms * 1e3, "bytes_per_row": sbpr,
+                     "frac_of_hbm_peak": rows * sbpr / sms / 1e6 / peak,
+                     "note": "timed with CUDA events around 10 calls; includes the 80-byte D2H of the statistics per call",
+                     "r_squared": float(1.0 - sstats[1] / max(sstats[3] - sstats[2] ** 2 / max(sstats[5], 1.0), 1e-300))}
+
     # ---- CPU baseline: sklearn on the host cores, bounded sample, rank 0 at N = 1 only --------------------
     cpu = None
     parity = None
@@ -405,6 +422,7 @@ def main() -> None:
             "data": "synthetic (device Philox, reference DGP: X~U(0,100), y=1+0.5*sum(X)+10*eps)",
             "config": workload_config(world, kind), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "variants": variants,
+            "companion_score": companion,
             "host_wall_ms_per_step": 1e3 * t_host / args.steps,
             "coef_head": [float(c) for c in coef[:3]], "intercept": float(b0),
         }

@@ -6,6 +6,7 @@
   c4      configs[3]: D = 32 rows streamed from pinned host DRAM through the C-ABI (B2_MEM_HOST); 200 M rows
           (26 GB pinned) stand in for 1 B (132 GB): the path is PCIe-bound, the rate does not depend on N
   c5      configs[4]: 30-day concept-drift replay, D = 1 reference-faithful tranches and a 1 M x 128 variant
+  refshape  the reference's one-feature shape at 1 B resident rows: masked fit + hold-out metrics (narrow kernels)
   shapes  device-resident Gram-kernel rate for D in {1, 8, 16, 32, 64, 128} x {f32, bf16}
 """
 from __future__ import annotations
@@ -119,6 +120,40 @@ def c5(ctx):
     print("c5", res, flush=True)
 
 
+def refshape(ctx):
+    """The reference's own shape (one feature, stage_1_train_model.py:95) at 1 B resident rows: train_model's two passes --
+    masked fit on the 80 % train rows, hold-out metrics on the other 20 % -- through the narrow kernels."""
+    n, d = 1_000_000_000, 1
+    X, y = ctx.synth(n, d, seed=4242)
+    mask = ctx.empty((n,), "u8")
+    blk = 100_000_000
+    pattern = (np.arange(blk, dtype=np.int64) % 5 != 0).astype(np.uint8)          # 80 / 20 membership
+    lib = b2.native.load()
+    for lo in range(0, n, blk):
+        b2.native._check(lib.b2_copy_h2d(ctx._h, mask.ptr + lo, pattern.ctypes.data, blk), "h2d")
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    est = b2.B200LinearRegression(ctx=ctx)
+    best_fit, best_score = 1e9, 1e9
+    for _ in range(4):
+        ctx.sync(); ctx.timer_start()
+        est.fit(X, y, row_mask=mask, mask_keep=1, with_spectrum=False)
+        best_fit = min(best_fit, ctx.timer_stop())
+        ctx.sync(); ctx.timer_start()
+        _, stats = ctx.score(X, est.coef_, float(est.intercept_), y=y, row_mask=mask, mask_keep=0, want_yhat=False)
+        best_score = min(best_score, ctx.timer_stop())
+    from bodywork_mlops_demo_b200 import stage_1_train_model as s1
+    mape, r2, mx = s1.metrics_from_stats(stats)
+    r = {"n": n, "d": d, "x": "f32 resident", "fit_ms": best_fit, "score_ms": best_score,
+         "fit_rows_per_s": n / best_fit * 1e3, "score_rows_per_s": n / best_score * 1e3,
+         "fit_hbm_gbs": n * 9 / best_fit / 1e6, "score_hbm_gbs": n * 9 / best_score / 1e6,
+         "bytes_per_row": "4 (x) + 4 (y) + 1 (mask) per pass", "coef": float(est.coef_[0]),
+         "intercept": float(est.intercept_), "test_rows": float(stats[5]), "MAPE": mape, "r_squared": r2,
+         "max_residual": mx}
+    X.free(); y.free(); mask.free()
+    out["reference_shape_1Bx1_train_model"] = r
+    print("refshape", r, flush=True)
+
+
 def shapes(ctx):
     res = []
     for d in (1, 8, 16, 32, 64, 128):
@@ -134,10 +169,10 @@ def shapes(ctx):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c3", "c4", "c5", "shapes"]
+    which = sys.argv[1:] or ["c3", "c4", "c5", "shapes", "refshape"]
     ctx = b2.Context(0)
     for w in which:
-        {"c3": c3, "c4": c4, "c5": c5, "shapes": shapes}[w](ctx)
+        {"c3": c3, "c4": c4, "c5": c5, "shapes": shapes, "refshape": refshape}[w](ctx)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     path = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
     prev = json.load(open(path)) if os.path.exists(path) else {}
