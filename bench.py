@@ -243,7 +243,16 @@ def main() -> None:
         import torch
         uid = [b2.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(world, rank, uid[0])
+        # NCCL may print its version banner on stdout; stdout carries exactly one JSON line, so park fd 1 on stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ctx.comm_init(world, rank, uid[0])
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
             # one-shot peer-memory exchange of S (NVLink stores + flags) instead of an NCCL launch per step
             try:
