@@ -44,6 +44,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    """dense bf16 TFLOP/s (burst) of this pool's B200s, driver-written; fallback = the profiling recipe's figure"""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh).get("bf16_tflops", 1688.7))
+    return 1688.7
+
+
 def ncu_traffic_per_launch(workload_key: str):
     """dram bytes per launch of the Gram kernel from the committed ncu capture, if one matches."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -324,6 +333,8 @@ def main() -> None:
     achieved = rows * bytes_per_row / (gram_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "gram_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
+                "mma_tflops_issued": rows * 2.0 * 128 * 144 * (2 if args.precision == "split" else 1) / gram_ms / 1e9
+                                     if D == 128 else None,
                 "algorithmic_bytes_per_row": bytes_per_row, "rows_per_launch": rows,
                 "kernel_ms_avg": gram_ms, "kernel_share_of_step": gram_ms / (ms / args.steps),
                 "traffic": ncu_traffic_per_launch(f"{kind}_{rows}x{D}")}
@@ -378,6 +389,10 @@ def main() -> None:
             variants[f"x_{vk}_operands_{'bf16x1' if vprec == 'bf16' else 'bf16x2'}"] = {
                 "fit_rows_per_s": rows / vms * 1e3, "gram_kernel_ms": kms / max(kl, 1),
                 "frac_of_hbm_peak": rows * bpr / (kms / max(kl, 1)) / 1e6 / peak,
+                # flops as issued to the MMA: 2 * 128 * 144 per row and operand (hi, and lo in split mode)
+                "mma_tflops_issued": rows * 2.0 * 128 * 144 * (1 if vprec == "bf16" else 2) / (kms / max(kl, 1)) / 1e9,
+                "frac_of_bf16_tensor_peak": rows * 2.0 * 128 * 144 * (1 if vprec == "bf16" else 2) / (kms / max(kl, 1))
+                                            / 1e9 / measured_tensor_peak(),
                 "coef_linf_vs_headline_fit": float(np.max(np.abs(cv - coef)))}
             ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
             if vk != kind:
