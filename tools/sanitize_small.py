@@ -25,4 +25,28 @@ if which in ("all", "score"):
     yh, st = ctx.score(Xd, np.full(128, 0.5), 1.0, y=yd, row_mask=md, mask_keep=0)
     print("score", st[5])
     Xs, ys = ctx.synth(1000, 128, seed=3); print("synth", float(Xs.to_host().mean()))
+if which in ("all", "narrow"):
+    # narrow-row Gram (one lane per row, two lanes per row, two rows per pair) and narrow-row scoring, with a mask
+    for d in (1, 3, 8, 12, 16):
+        Xn, yn = orc.generate_dataset(9000 + d, d, seed=10 + d, dtype=np.float32)
+        mn = (np.arange(len(yn)) % 4 != 0).astype(np.uint8)
+        Xnd, ynd, mnd = ctx.to_device(Xn), ctx.to_device(yn), ctx.to_device(mn)
+        ctx.set_kernel(b2.KERNEL_NARROW); ctx.gram_reset(d); ctx.gram_accumulate(Xnd, ynd, mnd, 1)
+        S = ctx.gram_export()
+        _, st = ctx.score(Xnd, np.full(d, 0.5), 1.0, y=ynd, row_mask=mnd, mask_keep=0)
+        print("narrow", d, S[d, d], st[5])
+        for a in (Xnd, ynd, mnd): a.free()
+    ctx.set_kernel(b2.KERNEL_AUTO)
+if which in ("all", "packed"):
+    # packed super-rows on the tcgen05 path (pack = 5 with the 2-D mask view, pack = 3) and the streaming scorer
+    for d in (24, 40, 64):
+        Xp, yp = orc.generate_dataset(6000 + d, d, seed=20 + d, dtype=np.float32)
+        mp = (np.arange(len(yp)) % 3 != 0).astype(np.uint8)
+        Xpd, ypd, mpd = ctx.to_device(Xp), ctx.to_device(yp), ctx.to_device(mp)
+        ctx.set_kernel(b2.KERNEL_TCGEN05); ctx.gram_reset(d); ctx.gram_accumulate(Xpd, ypd, mpd, 1)
+        S = ctx.gram_export()
+        _, st = ctx.score(Xpd, np.full(d, 0.5), 1.0, y=ypd, row_mask=mpd, mask_keep=0)
+        print("packed", d, S[d, d], st[5])
+        for a in (Xpd, ypd, mpd): a.free()
+    ctx.set_kernel(b2.KERNEL_AUTO)
 print("done")
