@@ -617,22 +617,30 @@ tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ sid
       red[kRedShiftOff + j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
     return;
   }
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // 64 elements per block, 4 threads per element: thread (e, q) sums the q-th quarter of the CTAs with 8 loads in
+  // flight (the loads are the latency), the quarters are combined in the fixed order 0..3 -> deterministic
+  __shared__ double quarter[4][64];
+  const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + e;
+  const int per = (n_ctas + 3) / 4;
+  const int c0 = q * per, c1 = (c0 + per < n_ctas) ? c0 + per : n_ctas;
   if (idx < kTcAccElems) {
-    double s0 = 0.0, s1 = 0.0;                       // two chains: the loads are the latency
-    int c = 0;
-    for (; c + 1 < n_ctas; c += 2) {
-      s0 += part[(size_t)c * kTcAccElems + idx];
-      s1 += part[(size_t)(c + 1) * kTcAccElems + idx];
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += part[(size_t)(c + u) * kTcAccElems + idx];
     }
-    if (c < n_ctas) s0 += part[(size_t)c * kTcAccElems + idx];
-    red[idx] = s0 + s1;
-  } else if (idx < kTcAccElems + 3) {
+    for (; c < c1; ++c) acc[0] += part[(size_t)c * kTcAccElems + idx];
+    quarter[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  } else if (idx < kTcAccElems + 3 && q == 0) {
     const int k = idx - kTcAccElems;
     double s = 0.0;
     for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k] + side[(size_t)c * kTcSideDoubles + 3 + k];
     red[idx] = s;
   }
+  __syncthreads();
+  if (q == 0 && idx < kTcAccElems) red[idx] = ((quarter[0][e] + quarter[1][e]) + quarter[2][e]) + quarter[3][e];
 }
 
 // finalize 2: one thread per element of S
@@ -862,7 +870,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   ctx->k_pairs += 1;
 
   const int red_elems = kTcAccElems + 3;
-  tc_reduce_kernel<<<(red_elems + kFinalizeThreads - 1) / kFinalizeThreads + 1, kFinalizeThreads, 0, ctx->stream>>>(
+  tc_reduce_kernel<<<(red_elems + 63) / 64 + 1, kFinalizeThreads, 0, ctx->stream>>>(
       ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n_in, d_in);
   B2_CUDA(cudaGetLastError());
   const int dp = d_in + 2;
