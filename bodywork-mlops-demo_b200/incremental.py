@@ -19,7 +19,7 @@ import os
 import time
 from dataclasses import dataclass, field
 from datetime import date
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import numpy as np
 
