@@ -32,6 +32,52 @@ def test_library_exports_every_declared_symbol():
     assert sorted(b2.native.EXPORTED_SYMBOLS) == declared
 
 
+def _header_prototypes():
+    """name -> list of parameter type strings, parsed from include/b2gram.h"""
+    text = open(os.path.join(ROOT, "include", "b2gram.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s+(b2_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = [p.strip() for p in m.group(2).split(",")]
+        if params == ["void"]:
+            params = []
+        protos[m.group(1)] = params
+    return protos
+
+
+def _ctype_class(param: str) -> str:
+    """coarse class of a C parameter: what the ctypes argtype must be compatible with"""
+    ptype = re.sub(r"\b[a-zA-Z_][a-zA-Z0-9_]*$", "", param).strip()       # drop the parameter name
+    if "*" in ptype:
+        return "pointer"
+    if "double" in ptype:
+        return "double"
+    if "int64_t" in ptype or "uint64_t" in ptype or "size_t" in ptype:
+        return "int64"
+    return "int32"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and coarse type class (pointer / 64-bit / 32-bit / double) of every binding == the C prototype."""
+    import ctypes as C
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(b2.native.EXPORTED_SYMBOLS)
+    for name, (_res, args) in b2.native._SIGNATURES.items():
+        params = protos[name]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, binding {len(args)}"
+        for param, ctype in zip(params, args):
+            want = _ctype_class(param)
+            if want == "pointer":
+                ok = ctype in (C.c_void_p, C.c_char_p) or hasattr(ctype, "contents") or issubclass(ctype, C._Pointer)
+            elif want == "double":
+                ok = ctype is C.c_double
+            elif want == "int64":
+                ok = C.sizeof(ctype) == 8 and ctype not in (C.c_double,)
+            else:
+                ok = C.sizeof(ctype) == 4 and ctype is not C.c_float
+            assert ok, f"{name}: parameter '{param}' bound as {ctype}"
+
+
 def test_abi_version_and_error_string():
     lib = b2.native.load()
     assert lib.b2_abi_version() == 1
