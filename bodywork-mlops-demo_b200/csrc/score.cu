@@ -21,32 +21,41 @@ constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr double kEpsF64 = 2.220446049250313e-16;
 
 constexpr int kNStats = 10;   // include/b2gram.h: b2_score stats_out layout
-// 1/x for x >= eps_f64 without the library's slow-path call: fp32 seed, two Newton steps in fp64
-__device__ __forceinline__ double rcp_pos(double x) {
-  double r = (double)__frcp_rn((float)x);
-#pragma unroll
-  for (int it = 0; it < 2; ++it) r = fma(r, fma(-x, r, 1.0), r);
-  return r;
-}
-
+// The per-row statistics are the fp64-pipe cost of scoring (they bind the narrow-row and bf16 kernels), so they are kept
+// to 13 fp64 instructions: one residual, one reciprocal refined by a single Newton step from the fp32 seed (the seed is
+// good to 2^-23, one step gives 2^-46 = 1.4e-14 relative -- the parity bar is 1e-12), fused multiply-adds for the four
+// second moments, the range test on the fp32 copy of |y|, and an integer row counter.
 struct RowStats {
-  double ape = 0.0, sse = 0.0, sy = 0.0, syy = 0.0, mx = 0.0, cnt = 0.0, sp = 0.0, spp = 0.0, syp = 0.0, mxape = 0.0;
-  __device__ void add(double y, double p) {
-    const double e = fabs(p - y);
+  double ape = 0.0, sse = 0.0, sy = 0.0, syy = 0.0, mx = 0.0, sp = 0.0, spp = 0.0, syp = 0.0, mxape = 0.0;
+  int rows = 0;
+  __device__ __forceinline__ double cnt() const { return (double)rows; }
+  __device__ __forceinline__ void add(double y, double p) {
+    const double r = y - p;
+    const double e = fabs(r);
     const double ay = fabs(y);
+    const float ayf = (float)ay;
     // |y| in the float range (the overwhelmingly common case): one cheap reciprocal serves both APE terms
-    const bool common = ay > 1e-30 && ay < 1e30;
-    const double term = common ? e * rcp_pos(ay) : e / fmax(ay, kEpsF64);
-    ape += term;                                  // sklearn MAPE term (stage_1_train_model.py:81)
-    sse += (y - p) * (y - p);
+    const bool common = ayf > 1e-30f && ayf < 1e30f;
+    double term, rel;
+    if (common) {
+      double rc = (double)__frcp_rn(ayf);
+      rc = fma(rc, fma(-ay, rc, 1.0), rc);
+      term = e * rc;
+      rel = term;
+    } else {
+      term = e / fmax(ay, kEpsF64);               // sklearn MAPE clamp (stage_1_train_model.py:81)
+      rel = e / ay;                               // |score/label - 1| (stage_4...:89,104); inf when label == 0
+    }
+    ape += term;
+    sse = fma(r, r, sse);
     sy += y;
-    syy += y * y;
+    syy = fma(y, y, syy);
     mx = fmax(mx, e);
-    cnt += 1.0;
+    rows += 1;
     sp += p;                                      // Pearson correlation terms (stage_4...:103 "r_squared")
-    spp += p * p;
-    syp += y * p;
-    mxape = fmax(mxape, common ? term : e / ay);  // |score/label - 1| (stage_4...:89,104); inf when label == 0
+    spp = fma(p, p, spp);
+    syp = fma(y, p, syp);
+    mxape = fmax(mxape, rel);
   }
 };
 __device__ __forceinline__ bool stat_is_max(int k) { return k == 4 || k == 9; }
@@ -145,7 +154,7 @@ score_kernel(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const doubl
   __shared__ double red[kScoreWarps][kNStats];
   if (lane == 0) {
     red[warp][0] = st.ape; red[warp][1] = st.sse; red[warp][2] = st.sy;  red[warp][3] = st.syy; red[warp][4] = st.mx;
-    red[warp][5] = st.cnt; red[warp][6] = st.sp;  red[warp][7] = st.spp; red[warp][8] = st.syp; red[warp][9] = st.mxape;
+    red[warp][5] = st.cnt(); red[warp][6] = st.sp;  red[warp][7] = st.spp; red[warp][8] = st.syp; red[warp][9] = st.mxape;
   }
   __syncthreads();
   if (threadIdx.x < kNStats) {
@@ -260,7 +269,7 @@ score_kernel_rows8(const T* __restrict__ X, int64_t n, int d, int64_t ldx, const
     }
   }
   // block reduce: first across the 4 row-owning lanes of each warp (lanes 0, 8, 16, 24), then across warps
-  double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+  double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt(), st.sp, st.spp, st.syp, st.mxape};
 #pragma unroll
   for (int k = 0; k < kNStats; ++k) {
 #pragma unroll
@@ -438,7 +447,7 @@ score_tma_kernel(const T* __restrict__ X, int n_tiles, int sweeps, int d, const 
       if (++s == kTmStages) { s = 0; phase ^= 1u; }
     }
     if (have) st.add((double)y_keep, p_keep);
-    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt(), st.sp, st.spp, st.syp, st.mxape};
 #pragma unroll
     for (int k = 0; k < kNStats; ++k) {
 #pragma unroll
@@ -553,7 +562,7 @@ score_narrow_kernel(const T* __restrict__ X, int n_tiles, int d, const double* _
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);
       if (++s == kSnStages) { s = 0; phase ^= 1u; }
     }
-    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt, st.sp, st.spp, st.syp, st.mxape};
+    double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt(), st.sp, st.spp, st.syp, st.mxape};
 #pragma unroll
     for (int k = 0; k < kNStats; ++k) {
 #pragma unroll
