@@ -1,6 +1,6 @@
 """GPU bring-up checks (development tool; run on the B200 box through gpurun).
 
-    python tools/gpu_check.py [stage ...]      stages: simt tc perf solve score host bf16
+    python tests/tools/gpu_check.py [stage ...]      stages: simt tc perf solve score host bf16
 
 Each stage runs in its own subprocess with a timeout so that a trapped kernel (sticky CUDA error)
 cannot take the later stages down.  Results are printed and appended to gpurun_out/gpu_check.log.
@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

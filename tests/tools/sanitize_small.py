@@ -1,6 +1,6 @@
 """Small driver for compute-sanitizer (memcheck / racecheck): every kernel once on small inputs."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import bodywork_mlops_demo_b200 as b2
 from oracle import ols_oracle as orc

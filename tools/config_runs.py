@@ -95,16 +95,20 @@ def c4(ctx):
 
 def c5(ctx):
     from bodywork_mlops_demo_b200 import incremental
-    from oracle import ols_oracle as orc     # data generator only (reference DGP, seeded)
     res = {}
     for tag, n, d, days in (("reference_tranches_1440x1", 1440, 1, 30), ("scaled_1Mx128", 1_000_000, 128, 10)):
         tranches = []
         for day in range(days):
-            if d == 1:
-                tranches.append(orc.generate_dataset(n, 1, seed=900 + day, alpha=orc.alpha_of_day(1 + day),
-                                                     drop_negative=True, dtype=np.float32))
+            alpha = 1.0 + 0.5 * np.sin(2.0 * np.pi * 6.0 * day / 364.0)       # stage_3...:33,38 intercept drift
+            if d == 1:                                                        # stage_3...:36-43 on the host, seeded
+                rng = np.random.RandomState(900 + day)
+                Xh = rng.uniform(0.0, 100.0, size=(n, 1))
+                yh = alpha + 0.5 * Xh[:, 0] + 10.0 * rng.normal(0.0, 1.0, size=n)
+                keep = yh >= 0                                                # dataset.query('y >= 0')
+                tranches.append((np.ascontiguousarray(Xh[keep], dtype=np.float32),
+                                 np.ascontiguousarray(yh[keep], dtype=np.float32)))
             else:
-                Xd, yd = ctx.synth(n, d, seed=900 + day, alpha=orc.alpha_of_day(1 + day))
+                Xd, yd = ctx.synth(n, d, seed=900 + day, alpha=alpha)
                 tranches.append((Xd.to_host(), yd.to_host()))
                 Xd.free(); yd.free()
         incremental.replay(tranches[:2], d, ctx=ctx)                      # warm-up
