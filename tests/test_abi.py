@@ -114,7 +114,9 @@ def test_library_has_blackwell_native_sass():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", b2.native.lib_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    # tcgen05 MMA / TMA tensor loads / TMEM loads+stores (gram_tc), TMA bulk copies and packed fp32 FMAs
+    # (gram_narrow, score kernels), mbarrier try_wait pipelines
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UBLKCP", "FFMA2", "SYNCS.PHASECHK.TRANS64.TRYWAIT"):
         assert mnemonic in sass, mnemonic
 
 
