@@ -318,9 +318,11 @@ class Context:
 
     # -- scoring ------------------------------------------------------------------------------------------
     def score(self, X, coef: np.ndarray, intercept: float, y=None, row_mask=None, mask_keep: int = 1,
-              want_yhat: bool = True):
+              want_yhat: bool = True, out=None):
         """Returns (yhat | None, stats | None); stats = the ten reductions of include/b2gram.h b2_score
-        ([sum_ape, sse, sum_y, sum_yy, max_abs_res, rows, sum_p, sum_pp, sum_yp, max_ape])."""
+        ([sum_ape, sse, sum_y, sum_yy, max_abs_res, rows, sum_p, sum_pp, sum_yp, max_ape]).
+        ``out``: a preallocated prediction buffer (DeviceArray f32 for device rows, float32 ndarray for host rows)
+        to write into instead of allocating one per call."""
         ptr, xdt, mk, n, d = _x_kind(X)
         coef = np.ascontiguousarray(coef, dtype=np.float64).ravel()
         if coef.size != d:
@@ -329,7 +331,17 @@ class Context:
         mp = _vec_ptr(row_mask, "u8", mk, n, "row_mask")
         yhat = None
         yhat_ptr = None
-        if want_yhat:
+        if out is not None:
+            if mk == MEM_DEVICE:
+                if not isinstance(out, DeviceArray) or out.kind != "f32" or int(np.prod(out.shape)) != n:
+                    raise RuntimeError("out must be an f32 DeviceArray with one element per row")
+                yhat, yhat_ptr = out, out.ptr
+            else:
+                if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.size == n
+                        and out.flags.c_contiguous):
+                    raise RuntimeError("out must be a C-contiguous float32 ndarray with one element per row")
+                yhat, yhat_ptr = out, out.ctypes.data
+        elif want_yhat:
             yhat = self.empty((n,), "f32") if mk == MEM_DEVICE else np.empty(n, dtype=np.float32)
             yhat_ptr = yhat.ptr if mk == MEM_DEVICE else yhat.ctypes.data
         stats = np.zeros(10, dtype=np.float64) if y is not None else None

@@ -457,6 +457,22 @@ def test_reference_shape_train_model_at_scale(ctx):
     X.free(); y.free(); mask.free()
 
 
+def test_score_into_a_preallocated_buffer(ctx):
+    X, y = orc.generate_dataset(30_000, 128, seed=77, dtype=np.float32)
+    coef = np.linspace(0.2, 0.8, 128)
+    Xd = ctx.to_device(X)
+    ref, _ = ctx.score(Xd, coef, 1.0)
+    out = ctx.empty((30_000,), "f32")
+    got, _ = ctx.score(Xd, coef, 1.0, out=out)
+    assert got is out and np.array_equal(out.to_host(), ref.to_host())
+    host_out = np.empty(30_000, dtype=np.float32)
+    got_h, _ = ctx.score(X, coef, 1.0, out=host_out)                   # host rows, host buffer
+    assert got_h is host_out and np.array_equal(host_out, ref.to_host())
+    with pytest.raises(RuntimeError):
+        ctx.score(Xd, coef, 1.0, out=np.empty(30_000, dtype=np.float32))
+    Xd.free(); ref.free(); out.free()
+
+
 def test_streaming_score_large_batch(ctx):
     """2 M x 128 device-resident rows (TMA ring + a 3-row register-fed tail) against the fp64 oracle."""
     n, d = 2_000_003, 128
