@@ -42,12 +42,15 @@ extern "C" {
 #define B2_MEM_HOST 1   /* host pointer (pinned preferred); streamed in row blocks */
 
 /* kernel selection for b2_gram_accumulate */
-#define B2_KERNEL_AUTO 0   /* tcgen05 path when shape/alignment allow, else CUDA-core */
+#define B2_KERNEL_AUTO 0   /* d <= 16: NARROW; wider: TCGEN05; odd layouts / tiny blocks: SIMT */
 #define B2_KERNEL_SIMT 1   /* fp64-accumulating CUDA-core kernel (any D <= 128)       */
 #define B2_KERNEL_TCGEN05 2 /* TMA -> smem -> bf16 hi/lo split -> tcgen05.mma -> TMEM   */
 #define B2_KERNEL_NARROW 3  /* D <= 16: TMA bulk-copy pipeline -> fp32 FMA on CUDA cores */
 /* tcgen05 path requirements: 4 <= d <= 128, row bytes and row pitch multiples of 16, X / y / row_mask 16-byte
- * aligned, n_rows >= 64.  Contiguous rows with d == 32 or 64 are packed 4 / 2 per 128-wide super-row. */
+ * aligned, n_rows >= 64.  Contiguous rows with 17 <= d <= 64 are packed min(5, 128 / d) per 128-wide super-row.
+ * narrow path requirements: d <= 16, contiguous rows (ldx == d), X / y / row_mask 16-byte aligned.
+ * AUTO uses NARROW from 4096 rows and TCGEN05 from 2048 rows per call; smaller blocks (the reference's 1 440-row
+ * daily tranche, stage_3_synthetic_data_generation.py:19) and every other layout take the exact fp64 SIMT kernel. */
 
 /* operand precision of the tcgen05 Gram kernel (b2_ctx_set_precision) */
 #define B2_PRECISION_SPLIT 0 /* bf16 hi + lo operands (16 mantissa bits), default: coef error ~2e-6 at any n */
