@@ -14,11 +14,14 @@ import numpy as np
 
 from . import build as _build
 
-F32, BF16 = 0, 1
+F32, BF16, F64 = 0, 1, 2
 MEM_DEVICE, MEM_HOST = 0, 1
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TCGEN05, KERNEL_NARROW = 0, 1, 2, 3
 PRECISION_SPLIT, PRECISION_BF16 = 0, 1
 E_SINGULAR = -4
+E_COMM = -5
+EXCHANGE_NONE, EXCHANGE_NCCL, EXCHANGE_PEER = 0, 1, 2
+ABI_VERSION = 2
 MAX_D = 128
 
 _c_i64 = C.c_int64
@@ -48,11 +51,17 @@ _SIGNATURES = {
     "b2_gram_allreduce": (C.c_int, [_vp]),
     "b2_gram_export": (C.c_int, [_vp, _vp, C.POINTER(_c_i64)]),
     "b2_gram_import": (C.c_int, [_vp, _vp, C.c_int]),
+    "b2_fit": (C.c_int, [_vp, _vp, C.c_int, _vp, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp,
+                         C.POINTER(C.c_double)]),
     "b2_solve": (C.c_int, [_vp, C.c_double, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "b2_solve_eigvals": (C.c_int, [_vp, C.c_double, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(_c_i64)]),
     "b2_solve_spectral": (C.c_int, [_vp, C.c_double, C.c_int, _vp, C.POINTER(C.c_double), _vp, C.POINTER(C.c_int)]),
     "b2_score": (C.c_int, [_vp, _vp, C.c_int, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_double, _vp, _vp,
                            C.c_int, _vp, _vp]),
     "b2_score_allreduce": (C.c_int, [_vp, _vp]),
+    "b2_metrics": (C.c_int, [_vp, _vp, _vp, C.c_int, _c_i64, C.c_int, _vp]),
+    "b2_synth_tranche": (C.c_int, [_vp, C.c_uint64, _c_i64, C.c_int, C.c_double, C.c_double, _vp, _vp,
+                                   C.POINTER(_c_i64)]),
     "b2_synth": (C.c_int, [_vp, C.c_uint64, _c_i64, _c_i64, C.c_int, _c_i64, C.c_int, C.c_double, C.c_double,
                            C.c_double, _vp, _vp]),
     "b2_comm_unique_id": (C.c_int, [C.c_char_p]),
@@ -62,6 +71,10 @@ _SIGNATURES = {
     "b2_comm_p2p_export": (C.c_int, [_vp, C.c_char_p]),
     "b2_comm_p2p_attach": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p]),
     "b2_comm_p2p_detach": (C.c_int, [_vp]),
+    "b2_comm_p2p_attach_local": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "b2_comm_set_timeout_ms": (C.c_int, [_vp, _c_i64]),
+    "b2_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b2_ctx_stats": (C.c_int, [_vp, C.POINTER(_c_i64)]),
     "b2_timer_start": (C.c_int, [_vp]),
     "b2_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "b2_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -95,7 +108,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.b2_abi_version() != 1:
+    if lib.b2_abi_version() != ABI_VERSION:
         raise RuntimeError("libb2gram.so ABI version mismatch")
     _lib = lib
     return lib
@@ -223,6 +236,7 @@ class Context:
         self._h = h.value
         self.device = int(device)
         self.d = 0
+        self.serial = 0      # bumped whenever the resident statistic S changes owner / content (estimators check it)
 
     # -- lifecycle -----------------------------------------------------------------------------
     def close(self) -> None:
@@ -272,6 +286,7 @@ class Context:
     def gram_reset(self, d: int) -> None:
         _check(load().b2_gram_reset(self._h, int(d)), "b2_gram_reset")
         self.d = int(d)
+        self.serial += 1
 
     def gram_accumulate(self, X, y, row_mask=None, mask_keep: int = 1) -> None:
         ptr, xdt, mk, n, d = _x_kind(X)
@@ -279,6 +294,7 @@ class Context:
             self.gram_reset(d)
         yp = _vec_ptr(y, "f32", mk, n, "y")
         mp = _vec_ptr(row_mask, "u8", mk, n, "row_mask")
+        self.serial += 1
         _check(load().b2_gram_accumulate(self._h, ptr, xdt, yp, n, d, d, mk, mp, int(mask_keep)),
                "b2_gram_accumulate")
 
@@ -296,6 +312,25 @@ class Context:
         d = S.shape[0] - 2
         _check(load().b2_gram_import(self._h, S.ctypes.data, d), "b2_gram_import")
         self.d = d
+        self.serial += 1
+
+    def fit(self, X, y, row_mask=None, mask_keep: int = 1, alpha: float = 0.0,
+            fit_intercept: bool = True) -> Tuple[np.ndarray, float]:
+        """The whole fit in one C call (b2_fit): reset + accumulate + all-reduce + solve.  Device-resident rows on the
+        tensor-core path run as two kernel launches.  Raises ``np.linalg.LinAlgError`` on a rank-deficient Gram."""
+        ptr, xdt, mk, n, d = _x_kind(X)
+        yp = _vec_ptr(y, "f32", mk, n, "y")
+        mp = _vec_ptr(row_mask, "u8", mk, n, "row_mask")
+        coef = np.empty(d, dtype=np.float64)
+        b0 = C.c_double(0.0)
+        rc = load().b2_fit(self._h, ptr, xdt, yp, n, d, d, mk, mp, int(mask_keep), float(alpha),
+                           int(bool(fit_intercept)), coef.ctypes.data, C.byref(b0))
+        self.d = int(d)
+        self.serial += 1
+        if rc == E_SINGULAR:
+            raise np.linalg.LinAlgError(last_error())
+        _check(rc, "b2_fit")
+        return coef, float(b0.value)
 
     # -- solve -----------------------------------------------------------------------------------------
     def solve(self, alpha: float = 0.0, fit_intercept: bool = True) -> Tuple[np.ndarray, float]:
@@ -316,7 +351,35 @@ class Context:
                                         C.byref(b0), sing.ctypes.data, C.byref(rank)), "b2_solve_spectral")
         return coef, float(b0.value), sing, int(rank.value)
 
+    def solve_eigvals(self, cond: float = 1e-6, fit_intercept: bool = True):
+        """(singular_, rank_, rows): sqrt of the eigenvalues of the centred Gram, descending (no eigenvectors)."""
+        sing = np.empty(self.d, dtype=np.float64)
+        rank, rows = C.c_int(0), _c_i64(0)
+        _check(load().b2_solve_eigvals(self._h, float(cond), int(bool(fit_intercept)), sing.ctypes.data,
+                                       C.byref(rank), C.byref(rows)), "b2_solve_eigvals")
+        return sing, int(rank.value), int(rows.value)
+
     # -- scoring ------------------------------------------------------------------------------------------
+    def metrics(self, y_actual, y_predicted) -> np.ndarray:
+        """The ten reductions of b2_score on two vectors (b2_metrics); float64 inputs stay float64."""
+        if isinstance(y_actual, DeviceArray):
+            if not isinstance(y_predicted, DeviceArray) or y_actual.kind != y_predicted.kind \
+                    or y_actual.kind not in ("f32", "f64") or y_actual.nbytes != y_predicted.nbytes:
+                raise RuntimeError("metrics: two device vectors of the same kind (f32 / f64) and length expected")
+            n = int(np.prod(y_actual.shape))
+            a_ptr, p_ptr, dt, mk = y_actual.ptr, y_predicted.ptr, (F32 if y_actual.kind == "f32" else F64), MEM_DEVICE
+        else:
+            dtype = np.float32 if (np.asarray(y_actual).dtype == np.float32 and
+                                   np.asarray(y_predicted).dtype == np.float32) else np.float64
+            a = np.ascontiguousarray(np.asarray(y_actual, dtype=dtype).ravel())
+            p = np.ascontiguousarray(np.asarray(y_predicted, dtype=dtype).ravel())
+            if a.size != p.size:
+                raise ValueError(f"Found input variables with inconsistent numbers of samples: [{a.size}, {p.size}]")
+            n, a_ptr, p_ptr, dt, mk = a.size, a.ctypes.data, p.ctypes.data, (F32 if dtype == np.float32 else F64), MEM_HOST
+        stats = np.zeros(10, dtype=np.float64)
+        _check(load().b2_metrics(self._h, a_ptr, p_ptr, dt, n, mk, stats.ctypes.data), "b2_metrics")
+        return stats
+
     def score(self, X, coef: np.ndarray, intercept: float, y=None, row_mask=None, mask_keep: int = 1,
               want_yhat: bool = True, out=None):
         """Returns (yhat | None, stats | None); stats = the ten reductions of include/b2gram.h b2_score
@@ -365,6 +428,21 @@ class Context:
                                y.ptr), "b2_synth")
         return X, y
 
+    def synth_tranche(self, n: int, day: int, seed: int = 1234, beta: float = 0.5, sigma: float = 10.0):
+        """One reference tranche (stage_3's generate_dataset: alpha(day), y >= 0 filter) -> (X (n, 1), y (n,), n_kept);
+        the buffers hold ``n`` rows, the first ``n_kept`` are valid."""
+        X = self.empty((n, 1), "f32")
+        y = self.empty((n,), "f32")
+        kept = _c_i64(0)
+        _check(load().b2_synth_tranche(self._h, int(seed), int(n), int(day), float(beta), float(sigma), X.ptr, y.ptr,
+                                       C.byref(kept)), "b2_synth_tranche")
+        return X, y, int(kept.value)
+
+    def stats(self) -> dict:
+        out = (_c_i64 * 3)()
+        _check(load().b2_ctx_stats(self._h, out), "b2_ctx_stats")
+        return {"fused_fits": int(out[0]), "peer_exchanges": int(out[1]), "launches": int(out[2])}
+
     # -- multi-GPU -----------------------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -392,6 +470,21 @@ class Context:
 
     def comm_p2p_detach(self) -> None:
         _check(load().b2_comm_p2p_detach(self._h), "b2_comm_p2p_detach")
+
+    @staticmethod
+    def comm_p2p_attach_local(contexts) -> None:
+        """Peer exchange between contexts of this process (rank = position in ``contexts``)."""
+        arr = (_vp * len(contexts))(*[c._h for c in contexts])
+        for rank, c in enumerate(contexts):
+            _check(load().b2_comm_p2p_attach_local(c._h, len(contexts), rank, arr), "b2_comm_p2p_attach_local")
+
+    def comm_set_timeout_ms(self, ms: int) -> None:
+        _check(load().b2_comm_set_timeout_ms(self._h, int(ms)), "b2_comm_set_timeout_ms")
+
+    def comm_info(self) -> dict:
+        n, r, e = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(load().b2_comm_info(self._h, C.byref(n), C.byref(r), C.byref(e)), "b2_comm_info")
+        return {"n_ranks": n.value, "rank": r.value, "exchange": {0: "none", 1: "nccl", 2: "p2p"}[e.value]}
 
     def comm_barrier(self) -> None:
         _check(load().b2_comm_barrier(self._h), "b2_comm_barrier")

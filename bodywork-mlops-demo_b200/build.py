@@ -40,15 +40,32 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile into a temporary file and rename it into place (a concurrent dlopen never sees a half-written library);
+    an exclusive file lock serialises the ranks of a torchrun launch, the late ones find the library fresh."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + sources() + ["-ldl"]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(PKG_DIR, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-6000:])
+    import fcntl
+    log = ""
+    with open(os.path.join(PKG_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():       # another process built it while we waited
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", tmp] + sources() + ["-ldl"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            log = proc.stdout + proc.stderr
+            log_tmp = os.path.join(PKG_DIR, f"build.log.{os.getpid()}.tmp")
+            with open(log_tmp, "w") as fh:
+                fh.write(" ".join(cmd) + "\n" + log)
+            os.replace(log_tmp, os.path.join(PKG_DIR, "build.log"))
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + log[-6000:])
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     if verbose:
         print(log)
     return LIB_PATH

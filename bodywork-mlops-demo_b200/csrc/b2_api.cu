@@ -2,12 +2,14 @@
 // helpers, dispatch between the tcgen05 and CUDA-core Gram kernels, host-streamed accumulation
 // (pinned ring -> HBM staging, copy/compute overlap), NCCL all-reduce of the statistic, timing.
 #include <dlfcn.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
 #include <new>
 
 #include "b2_internal.cuh"
+#include "b2_xchg.cuh"
 
 namespace b2 {
 
@@ -62,7 +64,7 @@ NcclApi* nccl() {
     int r_ = (call);                                                                           \
     if (r_ != 0) {                                                                             \
       set_error("%s failed: %s", #call, (api)->GetErrorString ? (api)->GetErrorString(r_) : "?"); \
-      return B2_E_NCCL;                                                                        \
+      return B2_E_COMM;                                                                        \
     }                                                                                          \
   } while (0)
 
@@ -85,10 +87,23 @@ int check_shape(b2_ctx* ctx, int x_dtype, int64_t n, int d, int64_t ldx, int mem
   return B2_OK;
 }
 
+constexpr int64_t kMaxRowsPerLaunch = (int64_t)1 << 30;   // TMA coordinates / tile counters are int32
+
 // One device-resident block through the selected Gram kernel.
 int gram_block(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
                const uint8_t* mask, int keep) {
   if (n == 0) return B2_OK;
+  if (n > kMaxRowsPerLaunch) {   // more rows than one launch indexes: same kernel family, several launches
+    const int es = x_dtype == B2_F32 ? 4 : 2;
+    for (int64_t r0 = 0; r0 < n; r0 += kMaxRowsPerLaunch) {
+      const int64_t rows = n - r0 < kMaxRowsPerLaunch ? n - r0 : kMaxRowsPerLaunch;
+      if (int r = gram_block(ctx, static_cast<const char*>(X) + (size_t)r0 * ldx * es, x_dtype, y + r0, rows, d, ldx,
+                             mask != nullptr ? mask + r0 : nullptr, keep))
+        return r;
+    }
+    return B2_OK;
+  }
+  if (int r = ensure_s_cleared(ctx)) return r;
   const bool tc_ok = gram_tc_supported(X, x_dtype, y, n, d, ldx) &&
                      (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
   const bool nw_ok = gram_narrow_supported(X, x_dtype, y, n, d, ldx, mask);
@@ -144,6 +159,15 @@ int stage_rows_h2d(b2_ctx* ctx, int buf, const void* X, int es, const float* y, 
 }
 
 }  // namespace
+
+int ensure_s_cleared(b2_ctx* ctx) {
+  if (ctx->s_zero_pending) {
+    B2_CUDA(cudaMemsetAsync(ctx->S, 0, sizeof(double) * kMaxS * kMaxS, ctx->stream));
+    ctx->s_zero_pending = false;
+  }
+  return B2_OK;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -189,6 +213,12 @@ static int ctx_allocate(b2_ctx* ctx) {
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->coef_dev), sizeof(double) * (kMaxD + 1)));
   B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->solve_out), sizeof(double) * (2 * kMaxD + 8)));
   B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->solve_host), sizeof(double) * (2 * kMaxD + 8), cudaHostAllocDefault));
+  B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tc_sync), 64));
+  B2_CUDA(cudaMemset(ctx->tc_sync, 0, 64));
+  B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->xchg_status_host), 64, cudaHostAllocDefault));
+  ctx->xchg_status_host[0] = 0u;
+  B2_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->coef_host), 2 * sizeof(double) * (kMaxD + 1), cudaHostAllocDefault));
+  for (int b = 0; b < 2; ++b) B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_coef[b], cudaEventDisableTiming));
   B2_CUDA(cudaMemset(ctx->S, 0, sizeof(double) * kMaxS * kMaxS));
   B2_CUDA(cudaMemset(ctx->tc_side, 0, sizeof(double) * (size_t)ctx->sm_count * kTcSideDoubles));
   B2_CUDA(cudaMemset(ctx->tc_red, 0, sizeof(double) * (kTcAccElems + 16 + kMaxD + 8)));
@@ -234,9 +264,12 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->xchg != nullptr) cudaFree(ctx->xchg);
   void* bufs[] = {ctx->S, ctx->tc_part, ctx->tc_side, ctx->tc_red, ctx->shift, ctx->simt_part, ctx->score_part,
                   ctx->coef_dev, ctx->solve_out, ctx->stage_x[0], ctx->stage_x[1], ctx->stage_y[0], ctx->stage_y[1],
-                  ctx->stage_m[0], ctx->stage_m[1]};
+                  ctx->stage_m[0], ctx->stage_m[1], ctx->yhat_stage[0], ctx->yhat_stage[1], ctx->tc_sync, ctx->synth_count};
   for (void* p : bufs) if (p != nullptr) cudaFree(p);
   if (ctx->solve_host != nullptr) cudaFreeHost(ctx->solve_host);
+  if (ctx->xchg_status_host != nullptr) cudaFreeHost(ctx->xchg_status_host);
+  if (ctx->coef_host != nullptr) cudaFreeHost(ctx->coef_host);
+  for (int b = 0; b < 2; ++b) if (ctx->ev_coef[b]) cudaEventDestroy(ctx->ev_coef[b]);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
     if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
@@ -335,7 +368,7 @@ int b2_gram_reset(b2_ctx* ctx, int d) {
   if (int r = use_device(ctx)) return r;
   if (d < 1 || d > kMaxD) { set_error("d=%d out of range [1,%d]", d, kMaxD); return B2_E_ARG; }
   ctx->d = d;
-  B2_CUDA(cudaMemsetAsync(ctx->S, 0, sizeof(double) * kMaxS * kMaxS, ctx->stream));
+  ctx->s_zero_pending = true;   // cleared (or overwritten) by the first kernel that adds to S: one launch less per fit
   return B2_OK;
 }
 
@@ -355,7 +388,8 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
   int64_t blk = 0;
   int rc = B2_OK;
   auto step = [&](int64_t r0, int buf, int64_t rows) -> int {
-    if (blk >= 2) B2_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
+    // a kernel of this call -- or of an EARLIER call that returned without a stream sync -- may still read this block
+    if (ctx->ev_consumed_valid[buf]) B2_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
     if (int r = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx)) return r;
     B2_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
     B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
@@ -363,6 +397,7 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
                            row_mask ? ctx->stage_m[buf] : nullptr, mask_keep))
       return r;
     B2_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+    ctx->ev_consumed_valid[buf] = true;
     return B2_OK;
   };
   for (int64_t r0 = 0; r0 < n_rows && rc == B2_OK; r0 += ctx->stage_rows, ++blk) {
@@ -376,13 +411,37 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
   return B2_OK;
 }
 
+// The peer-memory exchange reports a peer that did not deliver within the timeout through a status word in the
+// exchange buffer; it is read together with the next result the host fetches, so a late or dead rank turns into
+// B2_E_COMM instead of a fit on a partial statistic.  Call after the stream has been synchronised.
+static int queue_exchange_status_read(b2_ctx* ctx) {
+  if (!ctx->xchg_pending || ctx->xchg == nullptr) return B2_OK;
+  B2_CUDA(cudaMemcpyAsync(ctx->xchg_status_host, xchg_flags(ctx->xchg) + kXchgStatusWord, sizeof(unsigned int),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  return B2_OK;
+}
+static int check_exchange_status(b2_ctx* ctx) {
+  if (!ctx->xchg_pending || ctx->xchg == nullptr) return B2_OK;
+  ctx->xchg_pending = false;
+  const unsigned int st = ctx->xchg_status_host[0];
+  if (st != 0u) {
+    ctx->xchg_status_host[0] = 0u;
+    cudaMemsetAsync(xchg_flags(ctx->xchg) + kXchgStatusWord, 0, sizeof(unsigned int), ctx->stream);
+    set_error("peer-memory exchange %u timed out after %.1f s: a rank did not deliver its partial statistic "
+              "(S on this rank is incomplete)", st, (double)ctx->xchg_timeout_ns * 1e-9);
+    return B2_E_COMM;
+  }
+  return B2_OK;
+}
+
 int b2_gram_allreduce(b2_ctx* ctx) {
   if (int r = use_device(ctx)) return r;
   if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
+  if (int r = ensure_s_cleared(ctx)) return r;
   if (ctx->n_ranks > 1 && ctx->p2p_ready) return launch_p2p_allreduce(ctx);   // peer-memory one-shot exchange
-  if (ctx->n_ranks == 1 || ctx->comm == nullptr) return B2_OK;
+  if (ctx->comm == nullptr) return B2_OK;
   NcclApi* api = nccl();
-  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
+  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_COMM; }
   const size_t count = (size_t)(ctx->d + 2) * (ctx->d + 2);
   B2_NCCL(api, api->AllReduce(ctx->S, ctx->S, count, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
   return B2_OK;
@@ -393,8 +452,11 @@ int b2_gram_export(b2_ctx* ctx, double* S_out, int64_t* n_rows_out) {
   if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
   const int dp = ctx->d + 2;
   if (S_out == nullptr) { set_error("S_out is null"); return B2_E_ARG; }
+  if (int r = ensure_s_cleared(ctx)) return r;
   B2_CUDA(cudaMemcpyAsync(S_out, ctx->S, sizeof(double) * dp * dp, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int r = queue_exchange_status_read(ctx)) return r;
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (int r = check_exchange_status(ctx)) return r;
   if (n_rows_out != nullptr) *n_rows_out = (int64_t)(S_out[ctx->d * dp + ctx->d] + 0.5);
   return B2_OK;
 }
@@ -403,6 +465,7 @@ int b2_gram_import(b2_ctx* ctx, const double* S_in, int d) {
   if (int r = use_device(ctx)) return r;
   if (d < 1 || d > kMaxD || S_in == nullptr) { set_error("bad arguments to b2_gram_import"); return B2_E_ARG; }
   ctx->d = d;
+  ctx->s_zero_pending = false;
   B2_CUDA(cudaMemsetAsync(ctx->S, 0, sizeof(double) * kMaxS * kMaxS, ctx->stream));
   B2_CUDA(cudaMemcpyAsync(ctx->S, S_in, sizeof(double) * (d + 2) * (d + 2), cudaMemcpyHostToDevice, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -410,10 +473,15 @@ int b2_gram_import(b2_ctx* ctx, const double* S_in, int d) {
 }
 
 // ---- solve ------------------------------------------------------------------------------------------
-static int fetch_solution(b2_ctx* ctx, double* coef, double* intercept, double* singular, int* rank, double* info) {
+// from_pinned: the Cholesky kernel has written its result into ctx->solve_host itself (no copy node to wait for)
+static int fetch_solution(b2_ctx* ctx, bool from_pinned, double* coef, double* intercept, double* singular, int* rank,
+                          double* info) {
   double* host = ctx->solve_host;
-  B2_CUDA(cudaMemcpyAsync(host, ctx->solve_out, sizeof(double) * (2 * kMaxD + 8), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!from_pinned)
+    B2_CUDA(cudaMemcpyAsync(host, ctx->solve_out, sizeof(double) * (2 * kMaxD + 8), cudaMemcpyDeviceToHost, ctx->stream));
+  if (int r = queue_exchange_status_read(ctx)) return r;
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (int r = check_exchange_status(ctx)) return r;
   if (coef != nullptr) memcpy(coef, host, sizeof(double) * ctx->d);
   if (intercept != nullptr) *intercept = host[kMaxD];
   *info = host[kMaxD + 1];
@@ -422,36 +490,111 @@ static int fetch_solution(b2_ctx* ctx, double* coef, double* intercept, double* 
   return B2_OK;
 }
 
-int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double* intercept) {
-  if (int r = use_device(ctx)) return r;
-  if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
-  if (!(alpha >= 0.0)) { set_error("alpha must be >= 0"); return B2_E_ARG; }
-  if (int r = launch_solve_cholesky(ctx, alpha, fit_intercept)) return r;
+static int finish_cholesky(b2_ctx* ctx, double* coef, double* intercept) {
   double info = 0.0;
 #ifdef B2_DEV_KNOBS
   double phase[kMaxD];
-  if (int r = fetch_solution(ctx, coef, intercept, getenv("B2_SOLVE_TIMING") ? phase : nullptr, nullptr, &info)) return r;
+  if (int r = fetch_solution(ctx, true, coef, intercept, getenv("B2_SOLVE_TIMING") ? phase : nullptr, nullptr, &info)) return r;
   if (getenv("B2_SOLVE_TIMING"))
     fprintf(stderr, "[b2_solve] cycles: build %.0f diag %.0f panel %.0f update %.0f backward %.0f\n", phase[0], phase[1],
             phase[2], phase[3], phase[4]);
 #else
-  if (int r = fetch_solution(ctx, coef, intercept, nullptr, nullptr, &info)) return r;
+  if (int r = fetch_solution(ctx, true, coef, intercept, nullptr, nullptr, &info)) return r;
 #endif
+  if (info < 0.0) {
+    ctx->xchg_pending = false;
+    set_error("peer-memory exchange timed out after %.1f s inside the solve: a rank did not deliver its partial "
+              "statistic", (double)ctx->xchg_timeout_ns * 1e-9);
+    cudaMemsetAsync(xchg_flags(ctx->xchg) + kXchgStatusWord, 0, sizeof(unsigned int), ctx->stream);
+    return B2_E_COMM;
+  }
   if (info != 0.0) {
-    set_error("Cholesky pivot %d is not positive: the centred Gram matrix is rank deficient "
+    set_error("pivot %d of the LDL^T factorisation is not positive: the centred Gram matrix is rank deficient "
               "(use alpha > 0 or b2_solve_spectral)", (int)info);
     return B2_E_SINGULAR;
   }
   return B2_OK;
 }
 
+int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double* intercept) {
+  if (int r = use_device(ctx)) return r;
+  if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
+  if (!(alpha >= 0.0)) { set_error("alpha must be >= 0"); return B2_E_ARG; }
+  if (int r = ensure_s_cleared(ctx)) return r;
+  if (int r = launch_solve_cholesky(ctx, alpha, fit_intercept)) return r;
+  return finish_cholesky(ctx, coef, intercept);
+}
+
 int b2_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept, double* coef, double* intercept, double* singular,
                       int* rank) {
   if (int r = use_device(ctx)) return r;
   if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
+  if (int r = ensure_s_cleared(ctx)) return r;
   if (int r = launch_solve_spectral(ctx, cond, fit_intercept)) return r;
   double info = 0.0;
-  return fetch_solution(ctx, coef, intercept, singular, rank, &info);
+  return fetch_solution(ctx, false, coef, intercept, singular, rank, &info);
+}
+
+int b2_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept, double* singular, int* rank, int64_t* n_rows_out) {
+  if (int r = use_device(ctx)) return r;
+  if (ctx->d == 0) { set_error("b2_gram_reset has not been called"); return B2_E_STATE; }
+  if (int r = ensure_s_cleared(ctx)) return r;
+  if (int r = launch_solve_eigvals(ctx, cond, fit_intercept)) return r;
+  double info = 0.0;
+  if (int r = fetch_solution(ctx, false, nullptr, nullptr, singular, rank, &info)) return r;
+  if (n_rows_out != nullptr) *n_rows_out = (int64_t)(ctx->solve_host[kMaxD + 3 + kMaxD] + 0.5);
+  return B2_OK;
+}
+
+// ---- the whole fit in one call ----------------------------------------------------------------------------
+// reset + accumulate + all-reduce + solve.  Device-resident rows that take the tensor-core kernel run as TWO launches:
+// the Gram kernel (own shift sample, in-kernel reduce + fold of the per-CTA partials, S stored straight into the peers'
+// exchange slots) and the solve kernel (waits for the peers' slots, sums them, factors, writes the coefficients into
+// pinned host memory).  Everything else is the plain sequence of the four calls.
+int b2_fit(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_rows, int d, int64_t ldx, int mem_kind,
+           const uint8_t* row_mask, int mask_keep, double alpha, int fit_intercept, double* coef, double* intercept) {
+  if (int r = use_device(ctx)) return r;
+  if (int r = check_shape(ctx, x_dtype, n_rows, d, ldx, mem_kind)) return r;
+  if (!(alpha >= 0.0)) { set_error("alpha must be >= 0"); return B2_E_ARG; }
+  if (n_rows > 0 && (X == nullptr || y == nullptr)) { set_error("X / y is null"); return B2_E_ARG; }
+  static const bool no_fused = getenv("B2_NO_FUSED") != nullptr;      // diagnostic switch: the four-call sequence
+  bool fused = !no_fused && mem_kind == B2_MEM_DEVICE && n_rows <= kMaxRowsPerLaunch &&
+               gram_tc_supported(X, x_dtype, y, n_rows, d, ldx) &&
+               (row_mask == nullptr || (reinterpret_cast<uintptr_t>(row_mask) & 15) == 0);
+  if (fused) {
+    const bool nw_ok = gram_narrow_supported(X, x_dtype, y, n_rows, d, ldx, row_mask);
+    if (ctx->kernel_mode == B2_KERNEL_AUTO) fused = !(nw_ok && n_rows >= 4096) && n_rows >= 2048;
+    else fused = ctx->kernel_mode == B2_KERNEL_TCGEN05;
+  }
+  if (!fused) {
+    if (int r = b2_gram_reset(ctx, d)) return r;
+    if (int r = b2_gram_accumulate(ctx, X, x_dtype, y, n_rows, d, ldx, mem_kind, row_mask, mask_keep)) return r;
+    if (int r = b2_gram_allreduce(ctx)) return r;
+    return b2_solve(ctx, alpha, fit_intercept, coef, intercept);
+  }
+  ctx->d = d;
+  ctx->k_launches = 0;
+  const int es = x_dtype == B2_F32 ? 4 : 2;
+  const int64_t n_main = gram_tc_main_rows(n_rows, d, ldx, nullptr);
+  TcFuse fuse;
+  fuse.assign = 1; fuse.scatter = 0; fuse.epoch = 0;
+  if (n_main < n_rows) {   // the few rows the packed layout leaves over go in first; the fused fold then adds to S
+    ctx->s_zero_pending = true;
+    if (int r = ensure_s_cleared(ctx)) return r;
+    if (int r = launch_gram_simt(ctx, static_cast<const char*>(X) + (size_t)n_main * ldx * es, x_dtype, y + n_main,
+                                 n_rows - n_main, d, ldx, row_mask != nullptr ? row_mask + n_main : nullptr, mask_keep))
+      return r;
+    fuse.assign = 0;
+  }
+  const bool p2p = ctx->n_ranks > 1 && ctx->p2p_ready;
+  if (p2p) { fuse.scatter = 1; fuse.epoch = ++ctx->xchg_epoch; }
+  if (int r = launch_gram_tc(ctx, X, x_dtype, y, n_rows, d, ldx, row_mask, mask_keep, &fuse)) return r;
+  ctx->fused_fits += 1;
+  if (!p2p && ctx->comm != nullptr) {
+    if (int r = b2_gram_allreduce(ctx)) return r;
+  }
+  if (int r = launch_solve_cholesky(ctx, alpha, fit_intercept, p2p ? fuse.epoch : 0u)) return r;
+  return finish_cholesky(ctx, coef, intercept);
 }
 
 // ---- scoring ---------------------------------------------------------------------------------------
@@ -461,12 +604,19 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
   if (int r = use_device(ctx)) return r;
   if (int r = check_shape(ctx, x_dtype, n_rows, d, ldx, mem_kind)) return r;
   if (coef == nullptr || (n_rows > 0 && X == nullptr)) { set_error("coef / X is null"); return B2_E_ARG; }
-  double cbuf[kMaxD + 1];
-  memset(cbuf, 0, sizeof(cbuf));
-  memcpy(cbuf, coef, sizeof(double) * d);
-  cbuf[kMaxD] = intercept;
-  B2_CUDA(cudaMemcpyAsync(ctx->coef_dev, cbuf, sizeof(cbuf), cudaMemcpyHostToDevice, ctx->stream));
-  B2_CUDA(cudaStreamSynchronize(ctx->stream));  // cbuf is on this stack frame
+  // coefficients go up through one of two pinned slots (no stream sync per call: the slot is only waited for when it
+  // is reused, two calls later)
+  {
+    const int slot = ctx->coef_slot;
+    ctx->coef_slot ^= 1;
+    B2_CUDA(cudaEventSynchronize(ctx->ev_coef[slot]));
+    double* cbuf = ctx->coef_host + (size_t)slot * (kMaxD + 1);
+    memset(cbuf, 0, sizeof(double) * (kMaxD + 1));
+    memcpy(cbuf, coef, sizeof(double) * d);
+    cbuf[kMaxD] = intercept;
+    B2_CUDA(cudaMemcpyAsync(ctx->coef_dev, cbuf, sizeof(double) * (kMaxD + 1), cudaMemcpyHostToDevice, ctx->stream));
+    B2_CUDA(cudaEventRecord(ctx->ev_coef[slot], ctx->stream));
+  }
   double* acc = ctx->score_part + (size_t)ctx->score_ctas * 10;
   if (n_rows == 0) {
     B2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 10, ctx->stream));
@@ -475,16 +625,18 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
   } else {
     if (int r = ensure_staging(ctx)) return r;
     const int es = x_dtype == B2_F32 ? 4 : 2;
-    // predictions of a staged block land in a device block of their own and are copied back behind the kernel
+    // predictions of a staged block land in a device block of their own (allocated once per context) and are copied
+    // back behind the kernel
     float* yhat_dev[2] = {nullptr, nullptr};
     if (yhat != nullptr) {
       for (int b = 0; b < 2; ++b) {
-        if (cudaMalloc(reinterpret_cast<void**>(&yhat_dev[b]), (size_t)ctx->stage_rows * 4) != cudaSuccess) {
+        if (ctx->yhat_stage[b] == nullptr &&
+            cudaMalloc(reinterpret_cast<void**>(&ctx->yhat_stage[b]), (size_t)ctx->stage_rows * 4) != cudaSuccess) {
           cudaGetLastError();
-          if (yhat_dev[0] != nullptr) cudaFree(yhat_dev[0]);
           set_error("out of device memory for the prediction staging blocks");
           return B2_E_CUDA;
         }
+        yhat_dev[b] = ctx->yhat_stage[b];
       }
     }
     int64_t blk = 0;
@@ -492,7 +644,7 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
     for (int64_t r0 = 0; r0 < n_rows && rc == B2_OK; r0 += ctx->stage_rows, ++blk) {
       const int buf = (int)(blk & 1);
       const int64_t rows = (n_rows - r0 < ctx->stage_rows) ? n_rows - r0 : ctx->stage_rows;
-      if (blk >= 2) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
+      if (ctx->ev_consumed_valid[buf]) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
       rc = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx);
       if (rc != B2_OK) break;
       cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream);
@@ -503,10 +655,10 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
       if (yhat != nullptr)
         cudaMemcpyAsync(yhat + r0, yhat_dev[buf], (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->stream);
       cudaEventRecord(ctx->ev_consumed[buf], ctx->stream);
+      ctx->ev_consumed_valid[buf] = true;
     }
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
-    for (int b = 0; b < 2; ++b) if (yhat_dev[b]) cudaFree(yhat_dev[b]);
     if (rc != B2_OK) return rc;
     B2_CUDA(cudaGetLastError());
   }
@@ -520,11 +672,15 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
 int b2_score_allreduce(b2_ctx* ctx, double* stats) {
   if (int r = use_device(ctx)) return r;
   if (stats == nullptr) { set_error("stats is null"); return B2_E_ARG; }
-  if (ctx->n_ranks == 1 || ctx->comm == nullptr) return B2_OK;
+  if (ctx->comm == nullptr) {
+    if (ctx->n_ranks > 1) { set_error("b2_score_allreduce needs the NCCL communicator (b2_comm_init)"); return B2_E_STATE; }
+    return B2_OK;
+  }
   NcclApi* api = nccl();
-  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
+  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_COMM; }
   double* acc = ctx->score_part + (size_t)ctx->score_ctas * 10;   // 10 sums
   double* mx = acc + 10;                                          // 2 maxima
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous b2_score may still be reading its totals
   double host[10], hmax[2];
   memcpy(host, stats, sizeof(host));
   hmax[0] = host[4]; hmax[1] = host[9];
@@ -551,11 +707,85 @@ int b2_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n_rows, int
   return launch_synth(ctx, seed, row_offset, n_rows, d, ldx, x_dtype, alpha, beta, sigma, X_dev, y_dev);
 }
 
+// y >= 0 filtered one-feature tranche of day `day` (stage_3_synthetic_data_generation.py:28-43)
+int b2_synth_tranche(b2_ctx* ctx, uint64_t seed, int64_t n_rows, int day, double beta, double sigma, float* X_dev,
+                     float* y_dev, int64_t* n_kept_out) {
+  if (int r = use_device(ctx)) return r;
+  if (n_rows < 0 || day < 1 || n_kept_out == nullptr || (n_rows > 0 && (X_dev == nullptr || y_dev == nullptr))) {
+    set_error("bad arguments to b2_synth_tranche");
+    return B2_E_ARG;
+  }
+  if (ctx->synth_count == nullptr) B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->synth_count), 16));
+  // alpha(d) = kappa + amplitude * sin(2 pi f (d - 1) / 364), kappa = 1, amplitude = 0.5, f = 6  (stage_3...:31-33,38)
+  const double alpha = 1.0 + 0.5 * sin(2.0 * 3.14159265358979323846 * 6.0 * (double)(day - 1) / 364.0);
+  if (int r = launch_synth_tranche(ctx, seed, n_rows, alpha, beta, sigma, X_dev, y_dev,
+                                   reinterpret_cast<int64_t*>(ctx->synth_count)))
+    return r;
+  long long kept = 0;
+  B2_CUDA(cudaMemcpyAsync(&kept, ctx->synth_count, sizeof(kept), cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_kept_out = (int64_t)kept;
+  return B2_OK;
+}
+
+// ---- model_metrics on two vectors (stage_1_train_model.py:79-90), fp32 or fp64 inputs -------------------------
+int b2_metrics(b2_ctx* ctx, const void* y_actual, const void* y_predicted, int dtype, int64_t n_rows, int mem_kind,
+               double* stats_out) {
+  if (int r = use_device(ctx)) return r;
+  if (dtype != B2_F32 && dtype != B2_F64) { set_error("dtype must be B2_F32 or B2_F64"); return B2_E_ARG; }
+  if (n_rows < 0 || stats_out == nullptr || (n_rows > 0 && (y_actual == nullptr || y_predicted == nullptr))) {
+    set_error("bad arguments to b2_metrics");
+    return B2_E_ARG;
+  }
+  if (mem_kind != B2_MEM_DEVICE && mem_kind != B2_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return B2_E_ARG; }
+  double* acc = ctx->score_part + (size_t)ctx->score_ctas * 10;
+  const size_t es = dtype == B2_F32 ? 4 : 8;
+  if (n_rows == 0) {
+    B2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 10, ctx->stream));
+  } else if (mem_kind == B2_MEM_DEVICE) {
+    if (int r = launch_metrics(ctx, y_actual, y_predicted, dtype, n_rows, true)) return r;
+  } else {
+    // host vectors: blocks through the two staging buffers of the streamed paths (x block = y_actual, y block region
+    // is too small for fp64, so both vectors share the X block: [rows] actual then [rows] predicted)
+    if (int r = ensure_staging(ctx)) return r;
+    const int64_t blk_rows = (int64_t)(ctx->stage_bytes_x / (2 * es));
+    int64_t blk = 0;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += blk_rows, ++blk) {
+      const int buf = (int)(blk & 1);
+      const int64_t rows = n_rows - r0 < blk_rows ? n_rows - r0 : blk_rows;
+      if (ctx->ev_consumed_valid[buf]) B2_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
+      char* dst = static_cast<char*>(ctx->stage_x[buf]);
+      B2_CUDA(cudaMemcpyAsync(dst, static_cast<const char*>(y_actual) + (size_t)r0 * es, (size_t)rows * es,
+                              cudaMemcpyHostToDevice, ctx->copy_stream));
+      B2_CUDA(cudaMemcpyAsync(dst + (size_t)blk_rows * es, static_cast<const char*>(y_predicted) + (size_t)r0 * es,
+                              (size_t)rows * es, cudaMemcpyHostToDevice, ctx->copy_stream));
+      B2_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+      B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+      if (int r = launch_metrics(ctx, dst, dst + (size_t)blk_rows * es, dtype, rows, blk == 0)) return r;
+      B2_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+      ctx->ev_consumed_valid[buf] = true;
+    }
+    B2_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  }
+  B2_CUDA(cudaMemcpyAsync(stats_out, acc, sizeof(double) * 10, cudaMemcpyDeviceToHost, ctx->stream));
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B2_OK;
+}
+
+// counters of the context: [0] fits that took the fused two-launch path, [1] exchanges started, [2] kernels launched
+int b2_ctx_stats(b2_ctx* ctx, int64_t* out3) {
+  if (ctx == nullptr || out3 == nullptr) { set_error("null argument"); return B2_E_ARG; }
+  out3[0] = ctx->fused_fits;
+  out3[1] = (int64_t)ctx->xchg_epoch;
+  out3[2] = ctx->launches;
+  return B2_OK;
+}
+
 // ---- multi-GPU --------------------------------------------------------------------------------------------
 int b2_comm_unique_id(char* id_out) {
   if (id_out == nullptr) { set_error("id_out is null"); return B2_E_ARG; }
   NcclApi* api = nccl();
-  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
+  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_COMM; }
   NcclUid uid;
   B2_NCCL(api, api->GetUniqueId(&uid));
   memcpy(id_out, uid.internal, 128);
@@ -567,7 +797,7 @@ int b2_comm_init(b2_ctx* ctx, int n_ranks, int rank, const char* id) {
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks || id == nullptr) { set_error("bad communicator arguments"); return B2_E_ARG; }
   if (ctx->comm != nullptr) { set_error("communicator already initialised"); return B2_E_STATE; }
   NcclApi* api = nccl();
-  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
+  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_COMM; }
   NcclUid uid;
   memcpy(uid.internal, id, 128);
   B2_NCCL(api, api->CommInitRank(&ctx->comm, n_ranks, uid, rank));
@@ -586,18 +816,36 @@ int b2_comm_destroy(b2_ctx* ctx) {
   return B2_OK;
 }
 
-int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out) {
-  if (int r = use_device(ctx)) return r;
-  if (handle_out == nullptr) { set_error("handle_out is null"); return B2_E_ARG; }
+static int ensure_xchg(b2_ctx* ctx) {
   if (ctx->xchg == nullptr) {
     B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->xchg), kXchgBytes));
     B2_CUDA(cudaMemset(ctx->xchg, 0, kXchgBytes));
     B2_CUDA(cudaDeviceSynchronize());
   }
+  return B2_OK;
+}
+
+int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out) {
+  if (int r = use_device(ctx)) return r;
+  if (handle_out == nullptr) { set_error("handle_out is null"); return B2_E_ARG; }
+  if (int r = ensure_xchg(ctx)) return r;
   cudaIpcMemHandle_t h;
   B2_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
   memcpy(handle_out, &h, 64);
+  return B2_OK;
+}
+
+// A (re-)attached exchange starts at exchange number 0 on every rank: clear this rank's flags, ticket and status
+// (stale numbers from an earlier attachment would satisfy the first wait at once).  The caller's rendezvous must put
+// a barrier between the attach of all ranks and the first exchange -- peers write into this buffer.
+static int reset_exchange_words(b2_ctx* ctx) {
+  B2_CUDA(cudaStreamSynchronize(ctx->stream));
+  B2_CUDA(cudaMemset(xchg_flags(ctx->xchg), 0, 256));
+  B2_CUDA(cudaDeviceSynchronize());
+  ctx->xchg_epoch = 0;
+  ctx->xchg_pending = false;
+  ctx->xchg_status_host[0] = 0u;
   return B2_OK;
 }
 
@@ -608,6 +856,7 @@ int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles) 
     return B2_E_ARG;
   }
   if (ctx->p2p_ready) { set_error("peer exchange already attached"); return B2_E_STATE; }
+  if (int r = reset_exchange_words(ctx)) return r;
   for (int r = 0; r < n_ranks; ++r) {
     if (r == rank) { ctx->xchg_peer[r] = ctx->xchg; continue; }
     cudaIpcMemHandle_t h;
@@ -618,8 +867,42 @@ int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles) 
   }
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
-  ctx->xchg_epoch = 0;
   ctx->p2p_ready = true;
+  ctx->p2p_local = false;
+  return B2_OK;
+}
+
+// Same exchange between contexts of ONE process (a C client driving several GPUs, or two contexts on one GPU): the
+// peers' buffers are ordinary device pointers, reached through cudaDeviceEnablePeerAccess when the devices differ.
+int b2_comm_p2p_attach_local(b2_ctx* ctx, int n_ranks, int rank, b2_ctx* const* peers) {
+  if (int r = use_device(ctx)) return r;
+  if (n_ranks < 2 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks || peers == nullptr || peers[rank] != ctx) {
+    set_error("b2_comm_p2p_attach_local: bad arguments (2..%d contexts, peers[rank] == ctx)", kMaxRanks);
+    return B2_E_ARG;
+  }
+  if (ctx->p2p_ready) { set_error("peer exchange already attached"); return B2_E_STATE; }
+  for (int r = 0; r < n_ranks; ++r) {
+    if (peers[r] == nullptr) { set_error("peers[%d] is null", r); return B2_E_ARG; }
+    B2_CUDA(cudaSetDevice(peers[r]->device));
+    if (int rc = ensure_xchg(peers[r])) return rc;
+  }
+  B2_CUDA(cudaSetDevice(ctx->device));
+  if (int r = reset_exchange_words(ctx)) return r;
+  for (int r = 0; r < n_ranks; ++r) {
+    if (peers[r]->device != ctx->device) {
+      int can = 0;
+      B2_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peers[r]->device));
+      if (!can) { set_error("device %d cannot map the memory of device %d", ctx->device, peers[r]->device); return B2_E_UNSUPPORTED; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) B2_CUDA(e);
+      cudaGetLastError();
+    }
+    ctx->xchg_peer[r] = peers[r]->xchg;
+  }
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  ctx->p2p_ready = true;
+  ctx->p2p_local = true;
   return B2_OK;
 }
 
@@ -627,19 +910,37 @@ int b2_comm_p2p_detach(b2_ctx* ctx) {
   if (ctx == nullptr) { set_error("null context"); return B2_E_ARG; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->p2p_ready)
+  if (ctx->p2p_ready && !ctx->p2p_local)
     for (int r = 0; r < ctx->n_ranks; ++r)
       if (r != ctx->rank && ctx->xchg_peer[r] != nullptr) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
   for (int r = 0; r < kMaxRanks; ++r) ctx->xchg_peer[r] = nullptr;
+  if (ctx->p2p_ready && ctx->comm == nullptr) { ctx->n_ranks = 1; ctx->rank = 0; }
   ctx->p2p_ready = false;
+  ctx->p2p_local = false;
+  cudaGetLastError();
+  return B2_OK;
+}
+
+int b2_comm_set_timeout_ms(b2_ctx* ctx, int64_t ms) {
+  if (ctx == nullptr || ms < 1) { set_error("timeout must be >= 1 ms"); return B2_E_ARG; }
+  ctx->xchg_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return B2_OK;
+}
+
+int b2_comm_info(b2_ctx* ctx, int* n_ranks_out, int* rank_out, int* exchange_out) {
+  if (ctx == nullptr) { set_error("null context"); return B2_E_ARG; }
+  if (n_ranks_out != nullptr) *n_ranks_out = ctx->n_ranks;
+  if (rank_out != nullptr) *rank_out = ctx->rank;
+  if (exchange_out != nullptr)
+    *exchange_out = (ctx->n_ranks > 1 && ctx->p2p_ready) ? B2_EXCHANGE_PEER : (ctx->comm != nullptr ? B2_EXCHANGE_NCCL : B2_EXCHANGE_NONE);
   return B2_OK;
 }
 
 int b2_comm_barrier(b2_ctx* ctx) {
   if (int r = use_device(ctx)) return r;
-  if (ctx->n_ranks == 1 || ctx->comm == nullptr) return b2_ctx_sync(ctx);
+  if (ctx->comm == nullptr) return b2_ctx_sync(ctx);
   NcclApi* api = nccl();
-  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_NCCL; }
+  if (api == nullptr) { set_error("libnccl.so.2 could not be loaded"); return B2_E_COMM; }
   double* slot = ctx->tc_red + kTcAccElems + 8;  // spare scratch
   B2_NCCL(api, api->AllReduce(slot, slot, 1, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
   B2_CUDA(cudaStreamSynchronize(ctx->stream));

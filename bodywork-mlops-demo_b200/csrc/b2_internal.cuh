@@ -80,6 +80,10 @@ struct b2_ctx {
   double* score_part = nullptr;        // [score_ctas][6]
   int score_ctas = 0;
   double* coef_dev = nullptr;          // [kMaxD + 1]
+  double* coef_host = nullptr;         // pinned [2][kMaxD + 1]: upload slots of b2_score's coefficients
+  cudaEvent_t ev_coef[2] = {nullptr, nullptr};
+  int coef_slot = 0;
+  long long* synth_count = nullptr;    // device counter of b2_synth_tranche (rows kept by the y >= 0 filter)
   // solve scratch
   double* solve_out = nullptr;         // [kMaxD + 2 + kMaxD]: coef, intercept, info, singular
   double* solve_work = nullptr;        // [2 * kMaxD * kMaxD] eigenvectors etc.
@@ -91,6 +95,9 @@ struct b2_ctx {
   int64_t stage_rows = 0;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  bool ev_consumed_valid[2] = {false, false};   // a kernel of an earlier call may still read stage buffer b
+  float* yhat_stage[2] = {nullptr, nullptr};    // prediction staging blocks of the host-streamed b2_score
+  bool s_zero_pending = false;         // b2_gram_reset is lazy: S is cleared (or overwritten) by the first kernel that adds to it
   // NCCL
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -98,7 +105,14 @@ struct b2_ctx {
   double* xchg = nullptr;              // [2 parities][kMaxRanks][kMaxS*kMaxS] slots, then flags / ticket words
   double* xchg_peer[8] = {nullptr};    // this rank's view of every rank's exchange buffer (own entry == xchg)
   bool p2p_ready = false;
+  bool p2p_local = false;              // peers attached inside this process (b2_comm_p2p_attach_local): no IPC handles to close
   unsigned int xchg_epoch = 0;
+  unsigned long long xchg_timeout_ns = 10000000000ull;   // bound of the wait for a peer's flag (b2_comm_set_timeout_ms)
+  bool xchg_pending = false;           // an exchange was launched since the status word was last read
+  unsigned int* xchg_status_host = nullptr;  // pinned mirror of the exchange status word
+  // fused fit (b2_fit): in-kernel grid barrier / ticket words of the Gram kernel's reduce + fold tail
+  unsigned int* tc_sync = nullptr;     // [0], [1] barrier arrivals, [2] ticket
+  int fused_fits = 0;                  // fits that took the fused path (b2_ctx_stats)
 };
 
 namespace b2 {
@@ -107,18 +121,32 @@ namespace b2 {
 int launch_gram_simt(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
                      int64_t ldx, const uint8_t* mask, int keep);
 bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx);
+int64_t gram_tc_main_rows(int64_t n, int d, int64_t ldx, int* pack_out);
+// fuse != nullptr: the Gram kernel computes its own shift, reduces the per-CTA partials and folds them into S in the
+// same launch (grid barriers), and -- with an attached peer exchange -- stores S into every peer's slot (b2_fit)
+struct TcFuse {
+  int assign;                 // S = value instead of S += value (fresh statistic, no memset needed)
+  int scatter;                // 1: store the folded S into the exchange slots of all ranks and publish the flags
+  unsigned int epoch;         // exchange number when scatter == 1
+};
 int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
-                   int64_t ldx, const uint8_t* mask, int keep);
+                   int64_t ldx, const uint8_t* mask, int keep, const TcFuse* fuse = nullptr);
 bool gram_narrow_supported(const void* X, int x_dtype, const float* y, int64_t n, int d, int64_t ldx,
                            const uint8_t* mask);
 int launch_gram_narrow(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n, int d,
                        int64_t ldx, const uint8_t* mask, int keep);
-int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept);
+// gather_epoch != 0: the solve kernel first waits for the peer exchange `gather_epoch` and sums the slots into S
+int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept, unsigned int gather_epoch = 0);
+int launch_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept);
+int launch_metrics(b2_ctx* ctx, const void* y, const void* yhat, int dtype, int64_t n, bool first);
 int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept);
 int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx,
                  const float* y, const uint8_t* mask, int keep, float* yhat, bool first_block);
 int launch_p2p_allreduce(b2_ctx* ctx);
 int launch_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int d, int64_t ldx,
                  int x_dtype, double alpha, double beta, double sigma, void* X, float* y);
+int launch_synth_tranche(b2_ctx* ctx, uint64_t seed, int64_t n, double alpha, double beta, double sigma, float* X, float* y,
+                         int64_t* n_kept_dev);
+int ensure_s_cleared(b2_ctx* ctx);   // honours a lazy b2_gram_reset before a kernel that does S += ...
 
 }  // namespace b2

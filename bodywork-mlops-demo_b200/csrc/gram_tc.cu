@@ -34,6 +34,7 @@
 
 #include "b2_internal.cuh"
 #include "b2_ptx.cuh"
+#include "b2_xchg.cuh"
 
 namespace b2 {
 namespace {
@@ -167,6 +168,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 // ------------------------------------------------------------------------------------------
 constexpr int kShiftBlocks = 64;                 // partial sums of the row sample, one per block
 constexpr int kShiftStride = kMaxD + 1;          // floats per partial: features, then y (slot kMaxD)
+constexpr int kFusedSamples = 256;               // rows of the in-kernel shift sample (fused fit); <= kThreads
 
 __host__ __device__ __forceinline__ int64_t shift_samples(int64_t n) { return n < 2048 ? n : 2048; }
 
@@ -199,6 +201,140 @@ __global__ void tc_shift_kernel(const T* __restrict__ X, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// finalize, shared by the stand-alone kernels (tc_reduce_kernel / tc_fold_kernel: the b2_gram_accumulate path) and
+// by the fused tail of the Gram kernel (b2_fit): the same summation order in both, so the two paths agree bit for bit.
+//   red[col * 128 + i], col in [0, 288):  col < 144: D1 (A = hi), col >= 144: D2 (A = lo), columns of [hi | E]
+//   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
+// ------------------------------------------------------------------------------------------
+constexpr int kRedElems = kTcAccElems + 3;
+
+// Sum over the CTAs of elements [e0, e1) of the per-CTA partials.  4 threads per element: thread (e, q) sums the q-th
+// quarter of the CTAs with 8 loads in flight (the loads are the latency), the quarters are combined in the fixed order
+// 0..3 -> deterministic.  `quarter`: shared scratch of 4 * (blockDim.x / 4) doubles.  Call with the whole block.
+__device__ __forceinline__ void tc_reduce_range(const double* part, const double* side, int n_ctas, double* red,
+                                                int e0, int e1, double* quarter) {
+  const int epb = blockDim.x >> 2;                 // elements per pass
+  const int e = threadIdx.x % epb, q = threadIdx.x / epb;
+  const int per = (n_ctas + 3) / 4;
+  const int c0 = q * per, c1 = (c0 + per < n_ctas) ? c0 + per : n_ctas;
+  for (int base = e0; base < e1; base += epb) {
+    const int idx = base + e;
+    if (idx < e1 && idx < kTcAccElems) {
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int c = c0;
+      for (; c + 8 <= c1; c += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += __ldcg(part + (size_t)(c + u) * kTcAccElems + idx);
+      }
+      for (; c < c1; ++c) acc[0] += __ldcg(part + (size_t)c * kTcAccElems + idx);
+      quarter[q * epb + e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    } else if (idx < e1 && idx < kRedElems && q == 0) {
+      const int k = idx - kTcAccElems;
+      double s = 0.0;
+      for (int c = 0; c < n_ctas; ++c)
+        s += __ldcg(side + (size_t)c * kTcSideDoubles + k) + __ldcg(side + (size_t)c * kTcSideDoubles + 3 + k);
+      red[idx] = s;
+    }
+    __syncthreads();
+    if (q == 0 && idx < e1 && idx < kTcAccElems)
+      red[idx] = ((quarter[e] + quarter[epb + e]) + quarter[2 * epb + e]) + quarter[3 * epb + e];
+    __syncthreads();
+  }
+}
+
+// Grid-wide barrier of a co-resident (cooperatively launched) grid: arrive on a counter, wait until all CTAs have.
+// The counter is zeroed again by the kernel's final ticket.  Bounded: a protocol bug traps instead of hanging.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const uint64_t t0 = globaltimer_ns();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (seen < gridDim.x) {
+        __nanosleep(40);
+        if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+      }
+    } while (seen < gridDim.x);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// `pack` original rows share one 128-wide super-row (d * pack == 128 when pack > 1): original feature a of
+// sub-row blk is super-feature blk*d + a, and its E columns are 128 + 3*blk (+0 ones, +1 y'_hi, +2 y'_lo).
+// The true statistic is the sum over blk of the diagonal (blk, blk) blocks.
+// Returns the contribution of this launch to S[idx]; c[j] = the shift of feature j, c[kMaxD] = the shift of y
+// (fp64 copy in `red` for the stand-alone kernel, the CTA's fp32 smem copy in the fused tail -- the same values).
+template <typename CT>
+__device__ __forceinline__ double tc_fold_value(const double* red, const CT* c, int d, int pack, int idx) {
+  const int dp = d + 2;
+  const int a = idx / dp, b = idx % dp;
+  // D1[i][j] = red[j*128 + i], D2[i][j] = red[(144 + j)*128 + i]
+  auto D1 = [&](int i, int j) { return __ldcg(red + (size_t)j * kTcM + i); };
+  auto D2 = [&](int i, int j) { return __ldcg(red + (size_t)(kTcN + j) * kTcM + i); };
+  auto s1 = [&](int i) {                                                     // sum (x_i - c_i)
+    double t = 0.0;
+    for (int blk = 0; blk < pack; ++blk) t += D1(blk * d + i, 128 + 3 * blk) + D2(blk * d + i, 128 + 3 * blk);
+    return t;
+  };
+  auto sxy = [&](int i) {                                                    // sum (x_i - c_i) y'
+    double t = 0.0;
+    for (int blk = 0; blk < pack; ++blk) {
+      const int r = blk * d + i, e = 128 + 3 * blk;
+      t += D1(r, e + 1) + D1(r, e + 2) + D2(r, e + 1) + D2(r, e + 2);
+    }
+    return t;
+  };
+  const double sy = __ldcg(red + kTcAccElems + 0);
+  const double syy = __ldcg(red + kTcAccElems + 1);
+  const double n = __ldcg(red + kTcAccElems + 2);
+  const double cy = (double)c[kMaxD];
+  double val;
+  if (a < d && b < d) {
+    const double ca = (double)c[a], cb = (double)c[b];
+    // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hi.hi + lo.hi + hi.lo   (lo.lo dropped, ~2^-18 relative)
+    double g = 0.0;
+    for (int blk = 0; blk < pack; ++blk) {
+      const int ia = blk * d + a, ib = blk * d + b;
+      g += 0.5 * (D1(ia, ib) + D1(ib, ia)) + D2(ia, ib) + D2(ib, ia);
+    }
+    val = g + ca * s1(b) + cb * s1(a) + n * ca * cb;
+  } else if (a < d || b < d) {
+    const int i = a < d ? a : b;
+    const int o = a < d ? b : a;  // d (ones) or d+1 (y)
+    const double ci = (double)c[i];
+    if (o == d) val = s1(i) + n * ci;
+    else val = sxy(i) + cy * s1(i) + ci * sy + n * ci * cy;
+  } else if (a == d && b == d) {
+    val = n;
+  } else if (a == d + 1 && b == d + 1) {
+    val = syy + 2.0 * cy * sy + n * cy * cy;
+  } else {
+    val = sy + n * cy;
+  }
+  return val;
+}
+
+
+// what the fused tail needs (passed by value; fused == 0: the host launches tc_reduce_kernel / tc_fold_kernel)
+struct TcTail {
+  int fused;
+  int assign;                 // S = value instead of S += value
+  unsigned int* sync;         // [0], [1]: grid barriers, [2]: ticket
+  double* red;
+  double* S;
+  const void* X_raw;          // original rows for the in-kernel shift sample
+  const float* y_raw;
+  int64_t ldx_raw;
+  int n_ranks, rank;          // n_ranks > 1: scatter S to the peers' exchange slots and publish
+  unsigned int epoch;
+  PeerPtrs peers;
+};
+
+// ------------------------------------------------------------------------------------------
 // the Gram kernel
 // ------------------------------------------------------------------------------------------
 // DFIX = 128: feature count known at compile time (immediate smem offsets, no index arithmetic in
@@ -212,7 +348,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
                int64_t n_rows, int d_arg, int pack, int d_orig, int64_t n_shift, const float* __restrict__ shift,
                int chunk_tiles,
-               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg) {
+               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg,
+               const TcTail tail) {
 #ifdef B2_DEV_KNOBS
   const uint32_t dbg = dbg_arg;      // ablation switches (tools/build_dev.sh): results are WRONG when non-zero
 #else
@@ -275,9 +412,45 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
   // packed rows (pack > 1): super-row feature i < pack * d_orig is original feature i % d_orig -> the shift repeats;
   // the columns from pack * d_orig to 127 are TMA out-of-bounds zero fill and keep shift 0 (they contribute nothing)
-  for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
-    shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift)
-                              : (j < pack * d_orig ? shift_value(shift, j % d_orig, n_shift) : 0.f);
+  if (tail.fused) {
+    // fused fit: no separate shift kernel -- every CTA derives the same c from a strided sample of the original rows
+    // (kFusedSamples rows; any c near the column mean keeps the shifted Gram well conditioned, the fold is exact for
+    // every c).  The sample is 66 KB at D = 128: one DRAM read, L2 hits for the other 147 CTAs.
+    float* scratch = reinterpret_cast<float*>(smem + kOffRaw);          // [6 groups][128] + [24 warps]: raw stage 0 is idle
+    const int64_t samples = n_shift < kFusedSamples ? n_shift : kFusedSamples;
+    const int64_t stride = n_shift / samples;
+    const int col = threadIdx.x & 127, grp = threadIdx.x >> 7;          // 768 threads = 6 row groups x 128 columns
+    float acc = 0.f;
+    if (col < d_orig) {
+      const T* Xr = static_cast<const T*>(tail.X_raw);
+#pragma unroll 4
+      for (int64_t sidx = grp; sidx < samples; sidx += kThreads / 128)
+        acc += raw_ld_global<T>(Xr + sidx * stride * tail.ldx_raw + col);
+    }
+    scratch[grp * 128 + col] = acc;
+    float ya = (threadIdx.x < samples) ? __ldg(tail.y_raw + (int64_t)threadIdx.x * stride) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ya += __shfl_xor_sync(0xffffffffu, ya, o);
+    if (lane == 0) scratch[kThreads + warp] = ya;
+    __syncthreads();
+    float cval = 0.f;
+    if (threadIdx.x < 128) {
+      for (int g = 0; g < kThreads / 128; ++g) cval += scratch[g * 128 + threadIdx.x];
+      cval = threadIdx.x < d_orig ? __bfloat162float(__float2bfloat16_rn(cval / (float)samples)) : 0.f;
+    } else if (threadIdx.x == 128) {
+      for (int w = 0; w < kThreads / 32; ++w) cval += scratch[kThreads + w];
+      cval = __bfloat162float(__float2bfloat16_rn(cval / (float)samples));
+    }
+    __syncthreads();
+    if (threadIdx.x <= 128) scratch[threadIdx.x] = cval;                // [0, 128): c_j, [128]: c_y
+    __syncthreads();
+    for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
+      shift_s[j] = (j == kMaxD) ? scratch[128] : (j < pack * d_orig ? scratch[j % d_orig] : 0.f);
+  } else {
+    for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
+      shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift)
+                                : (j < pack * d_orig ? shift_value(shift, j % d_orig, n_shift) : 0.f);
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -544,6 +717,48 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
+  if (!tail.fused) return;
+
+  // ---- fused finalize (b2_fit): reduce the per-CTA partials, fold into S, scatter to the peers ---------------
+  // The grid is launched cooperatively (all CTAs co-resident), so a counter barrier is safe.  Every CTA's partial
+  // stores precede its arrival (the __syncthreads above orders the epilogue warps, the barrier fences).
+  double* quarter = reinterpret_cast<double*>(smem + kOffRaw);            // 4 * 192 doubles; the pipeline is drained
+  const int n_ctas = (int)gridDim.x;
+  grid_barrier(tail.sync + 0);
+  {
+    const int per = (((kRedElems + n_ctas - 1) / n_ctas) + 63) & ~63;
+    const int e0 = (int)blockIdx.x * per;
+    const int e1 = e0 + per < kRedElems ? e0 + per : kRedElems;
+    if (e0 < kRedElems) tc_reduce_range(part, side, n_ctas, tail.red, e0, e1, quarter);
+  }
+  grid_barrier(tail.sync + 1);
+  {
+    const int dp = d_orig + 2;
+    const int total = dp * dp;
+    const int per = (total + n_ctas - 1) / n_ctas;
+    const int i0 = (int)blockIdx.x * per;
+    const int i1 = i0 + per < total ? i0 + per : total;
+    const size_t slot = xchg_slot_offset(tail.epoch, tail.rank);
+    for (int idx = i0 + (int)threadIdx.x; idx < i1; idx += kThreads) {
+      const double val = tc_fold_value(tail.red, shift_s, d_orig, pack, idx);
+      const double sv = tail.assign ? val : tail.S[idx] + val;
+      tail.S[idx] = sv;
+      if (tail.n_ranks > 1) xchg_store_all(tail.peers, tail.n_ranks, slot, idx, sv);
+    }
+    if (tail.n_ranks > 1) __threadfence_system();
+  }
+  __syncthreads();
+  __shared__ bool last_cta;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_cta = (atomicAdd(tail.sync + 2, 1u) == gridDim.x - 1);
+    if (last_cta) {                       // every CTA has passed both barriers: re-arm them for the next launch
+      tail.sync[0] = 0u; tail.sync[1] = 0u; tail.sync[2] = 0u;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (last_cta && tail.n_ranks > 1) xchg_publish(tail.peers, tail.n_ranks, tail.rank, tail.epoch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -552,59 +767,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 //   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
 // tc_fold_kernel undoes the shift in fp64 and adds the result into the raw statistic S ((d+2)^2, stride d+2).
 // ------------------------------------------------------------------------------------------
-// `pack` original rows share one 128-wide super-row (d * pack == 128 when pack > 1): original feature a of
-// sub-row blk is super-feature blk*d + a, and its E columns are 128 + 3*blk (+0 ones, +1 y'_hi, +2 y'_lo).
-// The true statistic is the sum over blk of the diagonal (blk, blk) blocks.
-__device__ __forceinline__ void tc_fold_element(const double* __restrict__ red, const double* __restrict__ c,
-                                                int d, int pack, int idx, double* __restrict__ S) {
-  const int dp = d + 2;
-  const int a = idx / dp, b = idx % dp;
-  // D1[i][j] = red[j*128 + i], D2[i][j] = red[(144 + j)*128 + i]
-  auto D1 = [&](int i, int j) { return red[(size_t)j * kTcM + i]; };
-  auto D2 = [&](int i, int j) { return red[(size_t)(kTcN + j) * kTcM + i]; };
-  auto s1 = [&](int i) {                                                     // sum (x_i - c_i)
-    double t = 0.0;
-    for (int blk = 0; blk < pack; ++blk) t += D1(blk * d + i, 128 + 3 * blk) + D2(blk * d + i, 128 + 3 * blk);
-    return t;
-  };
-  auto sxy = [&](int i) {                                                    // sum (x_i - c_i) y'
-    double t = 0.0;
-    for (int blk = 0; blk < pack; ++blk) {
-      const int r = blk * d + i, e = 128 + 3 * blk;
-      t += D1(r, e + 1) + D1(r, e + 2) + D2(r, e + 1) + D2(r, e + 2);
-    }
-    return t;
-  };
-  const double sy = red[kTcAccElems + 0];
-  const double syy = red[kTcAccElems + 1];
-  const double n = red[kTcAccElems + 2];
-  const double cy = c[kMaxD];
-  double val;
-  if (a < d && b < d) {
-    const double ca = c[a], cb = c[b];
-    // G'(a,b) = sum (x_a-c_a)(x_b-c_b) ~= hi.hi + lo.hi + hi.lo   (lo.lo dropped, ~2^-18 relative)
-    double g = 0.0;
-    for (int blk = 0; blk < pack; ++blk) {
-      const int ia = blk * d + a, ib = blk * d + b;
-      g += 0.5 * (D1(ia, ib) + D1(ib, ia)) + D2(ia, ib) + D2(ib, ia);
-    }
-    val = g + ca * s1(b) + cb * s1(a) + n * ca * cb;
-  } else if (a < d || b < d) {
-    const int i = a < d ? a : b;
-    const int o = a < d ? b : a;  // d (ones) or d+1 (y)
-    const double ci = c[i];
-    if (o == d) val = s1(i) + n * ci;
-    else val = sxy(i) + cy * s1(i) + ci * sy + n * ci * cy;
-  } else if (a == d && b == d) {
-    val = n;
-  } else if (a == d + 1 && b == d + 1) {
-    val = syy + 2.0 * cy * sy + n * cy * cy;
-  } else {
-    val = sy + n * cy;
-  }
-  S[idx] += val;
-}
-
 constexpr int kFinalizeThreads = 256;
 constexpr int kRedShiftOff = kTcAccElems + 16;   // red[kRedShiftOff + j]: the shift c_j as fp64 (j = kMaxD: c_y)
 
@@ -617,37 +779,17 @@ tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ sid
       red[kRedShiftOff + j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
     return;
   }
-  // 64 elements per block, 4 threads per element: thread (e, q) sums the q-th quarter of the CTAs with 8 loads in
-  // flight (the loads are the latency), the quarters are combined in the fixed order 0..3 -> deterministic
-  __shared__ double quarter[4][64];
-  const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
-  const int idx = blockIdx.x * 64 + e;
-  const int per = (n_ctas + 3) / 4;
-  const int c0 = q * per, c1 = (c0 + per < n_ctas) ? c0 + per : n_ctas;
-  if (idx < kTcAccElems) {
-    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int c = c0;
-    for (; c + 8 <= c1; c += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += part[(size_t)(c + u) * kTcAccElems + idx];
-    }
-    for (; c < c1; ++c) acc[0] += part[(size_t)c * kTcAccElems + idx];
-    quarter[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  } else if (idx < kTcAccElems + 3 && q == 0) {
-    const int k = idx - kTcAccElems;
-    double s = 0.0;
-    for (int c = 0; c < n_ctas; ++c) s += side[(size_t)c * kTcSideDoubles + k] + side[(size_t)c * kTcSideDoubles + 3 + k];
-    red[idx] = s;
-  }
-  __syncthreads();
-  if (q == 0 && idx < kTcAccElems) red[idx] = ((quarter[0][e] + quarter[1][e]) + quarter[2][e]) + quarter[3][e];
+  __shared__ double quarter[4 * (kFinalizeThreads / 4)];
+  const int e0 = blockIdx.x * (kFinalizeThreads / 4);
+  const int e1 = e0 + kFinalizeThreads / 4 < kRedElems ? e0 + kFinalizeThreads / 4 : kRedElems;
+  tc_reduce_range(part, side, n_ctas, red, e0, e1, quarter);
 }
 
 // finalize 2: one thread per element of S
 __global__ void __launch_bounds__(kFinalizeThreads)
 tc_fold_kernel(const double* __restrict__ red, int d, int pack, double* __restrict__ S) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (d + 2) * (d + 2)) tc_fold_element(red, red + kRedShiftOff, d, pack, idx, S);
+  if (idx < (d + 2) * (d + 2)) S[idx] += tc_fold_value(red, red + kRedShiftOff, d, pack, idx);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -765,8 +907,21 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
   return B2_OK;
 }
 
+// Row packing rule: how many of the n rows the tensor-core launch covers (the rest, < 80 rows, take the CUDA-core kernel)
+int64_t gram_tc_main_rows(int64_t n_in, int d_in, int64_t ldx_in, int* pack_out) {
+  int pack = 1;
+  if (d_in > 16 && d_in <= 64 && ldx_in == d_in) {
+    pack = 128 / d_in;
+    if (pack > kMaxPack) pack = kMaxPack;
+    if (n_in < (int64_t)2 * kTcRows * pack) pack = 1;
+  }
+  const int group = pack == 1 ? 1 : (pack == 3 ? 48 : (pack == 5 ? 80 : 16));
+  if (pack_out != nullptr) *pack_out = pack;
+  return n_in - n_in % group;
+}
+
 int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_in, int d_in, int64_t ldx_in,
-                   const uint8_t* mask, int keep) {
+                   const uint8_t* mask, int keep, const TcFuse* fuse) {
   PFN_encodeTiled encode = get_encode();
   if (encode == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -779,13 +934,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   // multiple of lcm(pack, 16) rows (the y / mask views are 16-byte rows); the < 80 leftover rows go through the
   // CUDA-core kernel.
   int pack = 1;
-  if (d_in > 16 && d_in <= 64 && ldx_in == d_in) {
-    pack = 128 / d_in;
-    if (pack > kMaxPack) pack = kMaxPack;
-    if (n_in < (int64_t)2 * kTcRows * pack) pack = 1;
-  }
-  const int group = pack == 1 ? 1 : (pack == 3 ? 48 : (pack == 5 ? 80 : 16));
-  const int64_t n_main = n_in - n_in % group;          // original rows handled here
+  const int64_t n_main = gram_tc_main_rows(n_in, d_in, ldx_in, &pack);   // original rows handled here
   const int64_t n = n_main / pack;                      // super-rows
   const int d = pack > 1 ? 128 : d_in;                  // kernel feature count (DFIX = 128 when packed)
   const int d_tensor = d_in * pack;                     // columns that exist; the tile is zero-filled beyond them
@@ -824,13 +973,32 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     ctx->tc_attr_set = true;
   }
 
-  if (x_dtype == B2_F32)
-    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
-                                                                  ldx_in, ctx->shift);
-  else
-    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
-                                                                          n_in, d_in, ldx_in, ctx->shift);
-  B2_CUDA(cudaGetLastError());
+  const bool fused = fuse != nullptr;
+  if (!fused) {
+    if (int r = ensure_s_cleared(ctx)) return r;
+    if (x_dtype == B2_F32)
+      tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
+                                                                    ldx_in, ctx->shift);
+    else
+      tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
+                                                                            n_in, d_in, ldx_in, ctx->shift);
+    B2_CUDA(cudaGetLastError());
+  }
+  TcTail tail;
+  memset(&tail, 0, sizeof(tail));
+  tail.fused = fused ? 1 : 0;
+  tail.red = ctx->tc_red;
+  tail.S = ctx->S;
+  tail.sync = ctx->tc_sync;
+  tail.X_raw = X; tail.y_raw = y; tail.ldx_raw = ldx_in;
+  tail.n_ranks = 1;
+  if (fused) {
+    tail.assign = fuse->assign;
+    if (fuse->scatter) {
+      tail.n_ranks = ctx->n_ranks; tail.rank = ctx->rank; tail.epoch = fuse->epoch;
+      for (int r = 0; r < kMaxRanks; ++r) tail.peers.p[r] = ctx->xchg_peer[r];
+    }
+  }
 
 #ifdef B2_DEV_KNOBS
   static const uint32_t wait_ns = []() {   // development knob: suspend-time hint of the pipeline waits
@@ -850,11 +1018,21 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 #endif
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
-#define B2_LAUNCH_TC(T, DF, SP)                                                                          \
-  gram_tc_kernel<T, DF, SP><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                \
-      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 + m_map_2d : 0, keep, n, d, pack, d_in, n_in, ctx->shift, \
-      chunk_tiles,                                                                                        \
-      ctx->tc_part, ctx->tc_side, wait_ns, dbg)
+  // the fused variant needs every CTA co-resident (grid barriers): cooperative launch, 1 CTA per SM by construction
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = fused ? 1 : 0;
+  const int has_mask_arg = mask != nullptr ? 1 + m_map_2d : 0;
+  const float* shift_arg = ctx->shift;
+  double* part_arg = ctx->tc_part; double* side_arg = ctx->tc_side;
+  cudaError_t lerr = cudaSuccess;
+#define B2_LAUNCH_TC(T, DF, SP)                                                                                     \
+  lerr = cudaLaunchKernelEx(&cfg, gram_tc_kernel<T, DF, SP>, tmX, tmY, tmM, y_map_2d, has_mask_arg, keep, n, d, pack, \
+                            d_in, n_in, shift_arg, chunk_tiles, part_arg, side_arg, wait_ns, dbg, tail)
 #define B2_LAUNCH_TC_D(T, SP) \
   do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)
   const bool split = ctx->precision == B2_PRECISION_SPLIT;
@@ -865,21 +1043,27 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   }
 #undef B2_LAUNCH_TC_D
 #undef B2_LAUNCH_TC
+  B2_CUDA(lerr);
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][1], ctx->stream));
   ctx->k_pairs += 1;
 
-  const int red_elems = kTcAccElems + 3;
-  tc_reduce_kernel<<<(red_elems + 63) / 64 + 1, kFinalizeThreads, 0, ctx->stream>>>(
-      ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n_in, d_in);
-  B2_CUDA(cudaGetLastError());
-  const int dp = d_in + 2;
-  tc_fold_kernel<<<(dp * dp + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
-      ctx->tc_red, d_in, pack, ctx->S);
-  B2_CUDA(cudaGetLastError());
-  ctx->launches += 4;
-  ctx->k_launches += 4;
-  if (n_main < n_in) {   // the n % pack leftover rows
+  if (!fused) {
+    tc_reduce_kernel<<<(kRedElems + 63) / 64 + 1, kFinalizeThreads, 0, ctx->stream>>>(
+        ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n_in, d_in);
+    B2_CUDA(cudaGetLastError());
+    const int dp = d_in + 2;
+    tc_fold_kernel<<<(dp * dp + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
+        ctx->tc_red, d_in, pack, ctx->S);
+    B2_CUDA(cudaGetLastError());
+    ctx->launches += 4;
+    ctx->k_launches += 4;
+  } else {
+    ctx->launches += 1;
+    ctx->k_launches += 1;
+    ctx->s_zero_pending = false;   // the fold assigned (or added to an already cleared) S
+  }
+  if (n_main < n_in && !fused) {   // the n % pack leftover rows (the fused caller accumulates them first)
     const char* Xt = static_cast<const char*>(X) + (size_t)n_main * ldx_in * es;
     return launch_gram_simt(ctx, Xt, x_dtype, y + n_main, n_in - n_main, d_in, ldx_in,
                             mask != nullptr ? mask + n_main : nullptr, keep);

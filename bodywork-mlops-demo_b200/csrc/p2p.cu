@@ -1,78 +1,51 @@
 // p2p.cu -- one-shot all-reduce of the (D+2)^2 fp64 statistic over NVLink peer memory (no NCCL launch).
 //
 // The exchange step of the row-sharded fit: after the Gram kernel every rank
-// holds its partial S.  Each rank owns an exchange buffer that all peers have mapped through CUDA IPC:
+// holds its partial S.  Protocol and buffer layout: b2_xchg.cuh.
 //
-//   scatter kernel : every rank stores its S into slot[parity][rank] of EVERY rank's buffer (plain st.global on
-//                    peer pointers: NVLink 5 / NVSwitch), then -- after a system-scope fence and a last-block
-//                    ticket -- writes the epoch number into flag[rank] of every buffer;
-//   gather kernel  : spins (bounded) until all n flags in its own buffer carry this epoch, then sums the n slots
-//                    in rank order (bit-identical S on every rank, deterministic) into S.
+//   p2p_scatter_kernel : stores S into slot[parity][rank] of EVERY rank's buffer, then -- after a system-scope fence
+//                        and a last-block ticket -- publishes the exchange number in flag[rank] of every buffer;
+//   p2p_gather_kernel  : waits (bounded) until all n flags in its own buffer carry this exchange, then sums the n
+//                        slots in rank order (bit-identical S on every rank, deterministic) into S.  On a timeout it
+//                        leaves S alone and raises the status word, which the host reads with the next result it
+//                        fetches (b2_solve / b2_gram_export return B2_E_COMM instead of a fit on a partial statistic).
 //
-// Slots are double buffered by epoch parity: a rank can be at most one exchange ahead of a peer (its next gather
-// waits for that peer's next flag), so epoch k+1 data never overwrites slots a slow peer is still summing.
-// 135 KB per rank: latency bound -- the point is to remove the collective launch + protocol latency from a
-// ~1 ms step, and to keep compute (fold) and exchange in adjacent tiny kernels on one stream.
-#include "b2_internal.cuh"
+// These two launches serve the stand-alone b2_gram_allreduce call.  The fused fit (b2_fit, gram_tc.cu + solve.cu)
+// issues the same stores from the Gram kernel's fold and the same wait + sum from the solve kernel's prologue.
+#include "b2_xchg.cuh"
 
 namespace b2 {
 namespace {
 
-struct PeerPtrs { double* p[kMaxRanks]; };
-
-__host__ __device__ __forceinline__ unsigned int* flags_of(double* buf) {
-  return reinterpret_cast<unsigned int*>(buf + kXchgDataDoubles);
-}
-
 __global__ void p2p_scatter_kernel(const double* __restrict__ S, int n_elems, PeerPtrs peers, int n_ranks, int rank,
                                    unsigned int epoch) {
-  const size_t slot = ((size_t)(epoch & 1u) * kMaxRanks + rank) * kXchgSlotDoubles;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x) {
-    const double v = S[idx];
-#pragma unroll 1
-    for (int r = 0; r < n_ranks; ++r) peers.p[r][slot + idx] = v;      // r == rank: own buffer
-  }
+  const size_t slot = xchg_slot_offset(epoch, rank);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x)
+    xchg_store_all(peers, n_ranks, slot, idx, S[idx]);
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
   if (threadIdx.x == 0) {
-    unsigned int* ticket = flags_of(peers.p[rank]) + 32;               // own memory
+    unsigned int* ticket = xchg_flags(peers.p[rank]) + kXchgTicketWord;   // own memory
     last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     if (last) *ticket = 0u;
   }
   __syncthreads();
-  if (last && threadIdx.x < n_ranks) {
-    __threadfence_system();
-    volatile unsigned int* f = flags_of(peers.p[threadIdx.x]) + rank;  // "rank has delivered epoch"
-    *f = epoch;
-    __threadfence_system();
-  }
+  if (last) xchg_publish(peers, n_ranks, rank, epoch);
 }
 
 __global__ void p2p_gather_kernel(double* __restrict__ S, int n_elems, double* own, int n_ranks, unsigned int epoch,
-                                  int* __restrict__ status) {
+                                  unsigned long long timeout_ns) {
   __shared__ int ok;
   if (threadIdx.x == 0) {
-    volatile unsigned int* f = flags_of(own);
-    long long t0 = clock64();
-    int good = 1;
-    for (int r = 0; r < n_ranks && good; ++r) {
-      while ((int)(f[r] - epoch) < 0) {                                  // epochs are monotonic
-        if (clock64() - t0 > 4000000000ll) { good = 0; break; }          // ~2 s: a peer died -- do not hang
-      }
-    }
-    __threadfence_system();
-    ok = good;
-    if (!good && blockIdx.x == 0) *status = 1;
+    const bool good = xchg_wait(own, n_ranks, epoch, timeout_ns);
+    ok = good ? 1 : 0;
+    if (!good && blockIdx.x == 0) xchg_flags(own)[kXchgStatusWord] = epoch;
   }
   __syncthreads();
   if (!ok) return;
-  const size_t base = (size_t)(epoch & 1u) * kMaxRanks * kXchgSlotDoubles;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < n_ranks; ++r) s += __ldcg(own + base + (size_t)r * kXchgSlotDoubles + idx);   // bypass L1
-    S[idx] = s;
-  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_elems; idx += gridDim.x * blockDim.x)
+    S[idx] = xchg_sum(own, n_ranks, epoch, idx);
 }
 
 }  // namespace
@@ -84,10 +57,10 @@ int launch_p2p_allreduce(b2_ctx* ctx) {
   const unsigned int epoch = ++ctx->xchg_epoch;
   p2p_scatter_kernel<<<16, 256, 0, ctx->stream>>>(ctx->S, n_elems, peers, ctx->n_ranks, ctx->rank, epoch);
   B2_CUDA(cudaGetLastError());
-  int* status = reinterpret_cast<int*>(flags_of(ctx->xchg) + 48);
-  p2p_gather_kernel<<<16, 256, 0, ctx->stream>>>(ctx->S, n_elems, ctx->xchg, ctx->n_ranks, epoch, status);
+  p2p_gather_kernel<<<16, 256, 0, ctx->stream>>>(ctx->S, n_elems, ctx->xchg, ctx->n_ranks, epoch, ctx->xchg_timeout_ns);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 2;
+  ctx->xchg_pending = true;
   return B2_OK;
 }
 

@@ -57,6 +57,17 @@ struct RowStats {
     syp = fma(y, p, syp);
     mxape = fmax(mxape, rel);
   }
+  // same ten statistics with correctly rounded divisions (b2_metrics: parity with the float64 reference to rounding)
+  __device__ __forceinline__ void add_exact(double y, double p) {
+    const double r = y - p, e = fabs(r), ay = fabs(y);
+    ape += e / fmax(ay, kEpsF64);
+    sse = fma(r, r, sse);
+    sy += y; syy = fma(y, y, syy);
+    mx = fmax(mx, e);
+    rows += 1;
+    sp += p; spp = fma(p, p, spp); syp = fma(y, p, syp);
+    mxape = fmax(mxape, e / ay);
+  }
 };
 __device__ __forceinline__ bool stat_is_max(int k) { return k == 4 || k == 9; }
 
@@ -664,7 +675,57 @@ static int launch_score_narrow(b2_ctx* ctx, const T* X, int64_t n, int d, const 
   return launch_score_narrow_dp<T, 16>(ctx, X, n, d, y, mask, keep, yhat, first, done);
 }
 
+// ---- model_metrics on two vectors (stage_1_train_model.py:79-90): no X, no dot product -- the statistics alone, on
+// fp32 or fp64 inputs (the reference computes them on float64 arrays; b2_metrics(B2_F64) matches it to rounding) -----
+template <typename V>
+__global__ void __launch_bounds__(kScoreThreads)
+metrics_kernel(const V* __restrict__ ya, const V* __restrict__ yp, int64_t n, double* __restrict__ part) {
+  RowStats st;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) st.add_exact((double)ya[i], (double)yp[i]);
+  double v[kNStats] = {st.ape, st.sse, st.sy, st.syy, st.mx, st.cnt(), st.sp, st.spp, st.syp, st.mxape};
+  __shared__ double red[kScoreWarps][kNStats];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kNStats; ++k) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[k] = stat_is_max(k) ? fmax(v[k], other) : v[k] + other;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNStats; ++k) red[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNStats) {
+    const int k = threadIdx.x;
+    double acc = 0.0;
+    for (int w = 0; w < kScoreWarps; ++w) acc = stat_is_max(k) ? fmax(acc, red[w][k]) : acc + red[w][k];
+    part[(size_t)blockIdx.x * kNStats + k] = acc;
+  }
+}
+
 }  // namespace
+
+int launch_metrics(b2_ctx* ctx, const void* y, const void* yhat, int dtype, int64_t n, bool first) {
+  int64_t want = (n + kScoreThreads * 8 - 1) / (kScoreThreads * 8);
+  if (want < 1) want = 1;
+  const int grid = (int)(want < ctx->score_ctas ? want : ctx->score_ctas);
+  if (dtype == B2_F32)
+    metrics_kernel<float><<<grid, kScoreThreads, 0, ctx->stream>>>(static_cast<const float*>(y), static_cast<const float*>(yhat),
+                                                                   n, ctx->score_part);
+  else
+    metrics_kernel<double><<<grid, kScoreThreads, 0, ctx->stream>>>(static_cast<const double*>(y),
+                                                                    static_cast<const double*>(yhat), n, ctx->score_part);
+  B2_CUDA(cudaGetLastError());
+  score_reduce_kernel<<<1, 32, 0, ctx->stream>>>(ctx->score_part, grid, first ? 1 : 0,
+                                                 ctx->score_part + (size_t)ctx->score_ctas * kNStats);
+  B2_CUDA(cudaGetLastError());
+  ctx->launches += 2;
+  return B2_OK;
+}
 
 // ctx->score_part layout: [score_ctas][10] partials, then 10 doubles of running totals.
 int launch_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n, int d, int64_t ldx, const float* y,

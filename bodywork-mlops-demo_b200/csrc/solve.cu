@@ -13,6 +13,7 @@
 // One CTA: the matrices are <= 128 x 128 fp64 (132 KB with padding) -- latency bound, not a
 // throughput problem (D^3/3 = 0.7 MFLOP).
 #include "b2_internal.cuh"
+#include "b2_xchg.cuh"
 
 namespace b2 {
 namespace {
@@ -22,10 +23,12 @@ constexpr int kOutIntercept = kMaxD;      // solve_out layout: [0,d) coef | inte
 constexpr int kOutInfo = kMaxD + 1;
 constexpr int kOutRank = kMaxD + 2;
 constexpr int kOutSingular = kMaxD + 3;
+constexpr int kOutRows = kOutSingular + kMaxD;   // eigvals kernel only
 
 // Builds A (pitch d+1) and r in shared memory from the raw statistic; returns means.
-__device__ void build_normal_equations(const double* __restrict__ S, int d, double alpha, int fit_intercept,
+__device__ void build_normal_equations(const double* S_in, int d, double alpha, int fit_intercept,
                                        double* A, double* r, double* mean, double* ybar_out) {
+  const volatile double* S = S_in;   // the fused solve has just written S itself: plain loads, not the read-only path
   const int dp = d + 2, pitch = d + 1;
   const double n = S[d * dp + d];
   const double inv_n = n > 0.0 ? 1.0 / n : 0.0;
@@ -46,50 +49,77 @@ __device__ void build_normal_equations(const double* __restrict__ S, int d, doub
   __syncthreads();
 }
 
-// 1/sqrt(x) for normal positive x without the library's slow-path call (a call inside the unrolled pivot
-// loop forces the register-resident block onto the stack): scale x by an even power of two into [1, 4),
-// fp32 MUFU seed, two Newton steps in fp64 (2^-23 -> 2^-45 -> below 2^-53), undo the scaling.
-__device__ __forceinline__ double rsqrt_pos(double x) {
+// 1/x for normal positive x without the library's slow-path division (a call inside the unrolled pivot loop forces the
+// register-resident block onto the stack, and a correctly rounded fp64 division is ~25 dependent instructions):
+// scale x by a power of two into [1, 2), fp32 MUFU seed y0 (relative error e ~ 2^-22), one cubic step
+// y = y0 (1 + e + e^2) (error e^3 ~ 2^-66, i.e. below the rounding of the last FMA), undo the scaling.
+// 6 dependent instructions after the conversion; the pivot recurrence of the factorisation is paced by this chain.
+__device__ __forceinline__ double rcp_pos(double x) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int e2 = ((((hi >> 20) & 0x7ff) - 1023)) & ~1;                 // even exponent
-  const double xs = __hiloint2double(hi - (e2 << 20), lo);              // x * 2^-e2 in [1, 4)
-  double y = (double)rsqrtf((float)xs);
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double t = xs * y, h = 0.5 * y;
-    const double e = fma(-t, h, 0.5);
-    y = fma(y, e, y);
-  }
-  return __hiloint2double(__double2hiint(y) - ((e2 >> 1) << 20), __double2loint(y));   // y * 2^-(e2/2)
+  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  const double xs = __hiloint2double(hi - (e << 20), lo);               // x * 2^-e in [1, 2)
+  float y0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)xs));
+  double y = (double)y0;
+  const double er = fma(-xs, y, 1.0);
+  const double t = fma(er, er, er);
+  y = fma(y, t, y);
+  return __hiloint2double(__double2hiint(y) - (e << 20), __double2loint(y));   // y * 2^-e
 }
 
-// Blocked right-looking Cholesky (block 16) of the augmented matrix [A ; r^T]: carrying r as one extra
-// row through the panel/update steps leaves z = L^-1 r in that row, so no forward substitution is needed.
-// fp64 arithmetic on this part has ~25-cycle dependent latency, so every phase is written to keep the
-// dependent chains short:
-//   (1) diagonal block: one warp, rows in registers, pivots/multipliers by shuffle, no selects (the part of
-//       a row right of the diagonal may hold garbage -- it is never read), rsqrt_pos instead of sqrt/div;
-//   (2) panel: one thread per row, "right-looking" inside the row (2 dependent ops per column);
-//   (3) trailing update: 4 independent accumulators per thread;
-//   (4) back substitution per block in registers + shuffles.
-// A is (d+1) x (d+1) with row pitch d+1 (fp64, shared memory); row d = r^T.
+// Peer exchange consumed by the solve (fused fit, b2_fit): wait for the exchange, sum the slots into S.
+struct SolveXchg {
+  double* own;                  // nullptr: S is already complete
+  int n_ranks;
+  unsigned int epoch;
+  unsigned long long timeout_ns;
+};
+
+// Blocked right-looking LDL^T (block 16, no square roots) of the augmented matrix [A ; r^T]:  A = M D M^T with M unit
+// lower triangular.  Carrying r as one extra row through the panel / update steps leaves w = D^-1 M^-1 r in that row, so
+// there is no forward substitution; the back substitution M^T b = w needs no division.  fp64 arithmetic here is
+// latency bound (the whole solve is 0.7 MFLOP), so every phase is written to keep the dependent chains short:
+//   (1) diagonal block: one warp, rows in registers, pivots by shuffle; the products u_ik u_ck are formed before the
+//       reciprocal of the pivot arrives, so the recurrence pivot -> next pivot is shuffle + rcp_pos (6) + one FMA;
+//   (2) panel: one thread per row, 2 dependent operations per column;
+//   (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m] (U = M D, the unscaled entries): 2 x 4 register tiles;
+//   (4) back substitution per block in registers: shuffle + FMA per unknown.
+// A is (d+1) x (d+1) with row pitch d+1 (fp64, shared memory); row d = r^T.  U: (d+1) x 16 panel scratch.
 constexpr int kNB = 16;
 constexpr int kCholThreads = 512;
+constexpr int kUPitch = kNB + 1;
 
 __global__ void __launch_bounds__(kCholThreads, 1)
-solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit_intercept,
-                      double* __restrict__ out) {
+solve_cholesky_kernel(double* S, int d, double alpha, int fit_intercept, double* __restrict__ out, const SolveXchg xc) {
   extern __shared__ double sm[];
   const int pitch = d + 1;
   double* A = sm;                        // rows 0..d-1 = A, row d = r^T
   double* r = A + d * pitch;             // alias of row d
   double* mean = A + (d + 1) * pitch;    // d
-  double* invd = mean + d;               // d: 1 / L[k][k]
+  double* invd = mean + d;               // d: 1 / D[k]
   double* misc = invd + d;               // [0] ybar, [1] max diag, [2] info (1-based failing pivot, 0 = ok)
+  double* U = misc + 8;                  // (d+1) x kUPitch: unscaled panel entries of the current block column
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   long long tm[5] = {0, 0, 0, 0, 0};     // phase cycle counters: build, diag, panel, update, backward
   long long tc0 = clock64();
+  if (xc.own != nullptr) {
+    // fused fit: this rank's partial S went to every peer from the Gram kernel's fold; gather = wait + sum, here
+    __shared__ int ok;
+    if (tid == 0) ok = xchg_wait(xc.own, xc.n_ranks, xc.epoch, xc.timeout_ns) ? 1 : 0;
+    __syncthreads();
+    if (!ok) {
+      if (tid == 0) {
+        xchg_flags(xc.own)[kXchgStatusWord] = xc.epoch;
+        out[kOutInfo] = -1.0;             // the host turns this into B2_E_COMM (never a fit on a partial statistic)
+      }
+      return;
+    }
+    const int dp = d + 2;
+    for (int idx = tid; idx < dp * dp; idx += blockDim.x) S[idx] = xchg_sum(xc.own, xc.n_ranks, xc.epoch, idx);
+    __threadfence();
+    __syncthreads();
+  }
   build_normal_equations(S, d, alpha, fit_intercept, A, r, mean, &misc[0]);
   tm[0] = clock64() - tc0;
   if (warp == 0) {
@@ -106,63 +136,47 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
   for (int kb = 0; kb < d; kb += kNB) {
     const int nb = (d - kb) < kNB ? (d - kb) : kNB;
     tc0 = clock64();
-    // ---- (1) diagonal block -------------------------------------------------------------------------
+    // ---- (1) diagonal block: rows kb .. kb+nb-1 in the registers of lanes 0 .. nb-1 -------------------------------
     if (warp == 0) {
-      if (nb == kNB) {
-        double a[kNB];
-        const int row = kb + (lane & (kNB - 1));
+      double a[kNB], mm[kNB];
+      const int lrow = lane & (kNB - 1);
+      const int row = kb + (lrow < nb ? lrow : 0);
+      const bool act = lane < nb;
 #pragma unroll
-        for (int c = 0; c < kNB; ++c) a[c] = lane < kNB ? A[row * pitch + kb + c] : 0.0;   // only c <= lane is meaningful
-        double my_inv = 1.0;
-        int first_bad = 0;
+      for (int c = 0; c < kNB; ++c) { a[c] = (act && c < nb) ? A[row * pitch + kb + c] : 0.0; mm[c] = 0.0; }
+      double my_rc = 1.0;
+      int first_bad = 0;
 #pragma unroll
-        for (int k = 0; k < kNB; ++k) {
+      for (int k = 0; k < kNB; ++k) {
+        if (k < nb) {
           const double piv = __shfl_sync(0xffffffffu, a[k], k);
           const bool bad = !(piv > tiny);
-          const double inv = bad ? 1.0 : rsqrt_pos(piv);
-          const double l = a[k] * inv;                  // lane > k: L[r][k]; lane == k: sqrt(piv)
-          a[k] = l;
-          my_inv = (lane == k) ? inv : my_inv;
+          const double rc = bad ? 1.0 : rcp_pos(piv);
+          const double u = a[k];                        // lane > k: unscaled entry u_ik = m_ik * D_k
+          mm[k] = u * rc;                               // m_ik
+          my_rc = (lane == k) ? rc : my_rc;
           first_bad = (bad && first_bad == 0) ? (kb + k + 1) : first_bad;
 #pragma unroll
-          for (int c = k + 1; c < kNB; ++c) a[c] = fma(-l, __shfl_sync(0xffffffffu, l, c), a[c]);
-        }
-        __syncwarp();
-        if (lane < kNB) {
-#pragma unroll
-          for (int c = 0; c < kNB; ++c) if (c <= lane) A[row * pitch + kb + c] = a[c];
-          invd[kb + lane] = my_inv;
-        }
-        if (lane == 0 && first_bad != 0 && misc[2] == 0.0) misc[2] = (double)first_bad;
-      } else {   // ragged last block (d % 16 != 0): plain shared-memory version
-        const int row = kb + lane;
-        for (int k = 0; k < nb; ++k) {
-          const int kk = kb + k;
-          const double piv = A[kk * pitch + kk];
-          __syncwarp();
-          const bool bad = !(piv > tiny);
-          const double inv = bad ? 1.0 : rsqrt_pos(piv);
-          if (lane == k) {
-            if (bad && misc[2] == 0.0) misc[2] = (double)(kk + 1);
-            A[kk * pitch + kk] = bad ? 1.0 : piv * inv;
-            invd[kk] = inv;
+          for (int c = k + 1; c < kNB; ++c) {
+            const double uc = __shfl_sync(0xffffffffu, u, c);   // u_ck
+            a[c] = fma(-(u * uc), rc, a[c]);                    // a_ic -= u_ik u_ck / D_k   (only c <= lane is meaningful)
           }
-          double l = 0.0;
-          if (lane > k && lane < nb) {
-            l = A[row * pitch + kk] * inv;
-            A[row * pitch + kk] = l;
-          }
-          __syncwarp();
-          if (lane > k && lane < nb)
-            for (int c = k + 1; c <= lane; ++c) A[row * pitch + kb + c] -= l * A[(kb + c) * pitch + kk];
-          __syncwarp();
         }
       }
+      __syncwarp();
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+          if (c < lane) { A[row * pitch + kb + c] = mm[c]; U[row * kUPitch + c] = a[c]; }
+        }
+        invd[kb + lane] = my_rc;
+      }
+      if (lane == 0 && first_bad != 0 && misc[2] == 0.0) misc[2] = (double)first_bad;
     }
     __syncthreads();
     tm[1] += clock64() - tc0; tc0 = clock64();
     if (misc[2] != 0.0) break;
-    // ---- (2) panel: rows below the block (incl. the r row): x L_bb^T = a ----------------------------------
+    // ---- (2) panel: rows below the block (incl. the r row) ----------------------------------------------------------
     const int below = rows - kb - nb;
     for (int t = tid; t < below; t += blockDim.x) {
       const int i = kb + nb + t;
@@ -172,20 +186,20 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
 #pragma unroll
       for (int m = 0; m < kNB; ++m) {
         if (m < nb) {
-          const double xm = sv[m] * invd[kb + m];
-          sv[m] = xm;
+          const double um = sv[m];
+          const double xm = um * invd[kb + m];
+          A[i * pitch + kb + m] = xm;
+          U[i * kUPitch + m] = um;
 #pragma unroll
-          for (int c = m + 1; c < kNB; ++c) if (c < nb) sv[c] = fma(-xm, A[(kb + c) * pitch + kb + m], sv[c]);
+          for (int c = m + 1; c < kNB; ++c) if (c < nb) sv[c] = fma(-xm, U[(kb + c) * kUPitch + m], sv[c]);
         }
       }
-#pragma unroll
-      for (int c = 0; c < kNB; ++c) if (c < nb) A[i * pitch + kb + c] = sv[c];
     }
     __syncthreads();
     tm[2] += clock64() - tc0; tc0 = clock64();
-    // ---- (3) trailing update A[i][j] -= sum_m P[i][m] P[j][m], i >= j >= kb+nb (i up to the r row) -----------
+    // ---- (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m], i >= j >= kb+nb (i up to the r row) ---------------
     // each thread owns a 2-row x 4-column register tile: 8 independent fp64 chains, one shared-memory load per
-    // two FMAs (the panel rows P[i][.] stay in registers)
+    // two FMAs (the panel rows M[i][.] stay in registers)
     const int ty = tid >> 4, tx = tid & 15;           // 32 x 16 thread grid
     const int base = kb + nb;
     for (int i0 = base + ty; i0 < rows; i0 += 64) {
@@ -207,7 +221,7 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = j0 + 16 * u;
-            const double pj = (m < nb && j <= jmax) ? A[j * pitch + kb + m] : 0.0;
+            const double pj = (m < nb && j <= jmax) ? U[j * kUPitch + m] : 0.0;
             a0[u] = fma(p0[m], pj, a0[u]);
             a1[u] = fma(p1[m], pj, a1[u]);
           }
@@ -226,32 +240,25 @@ solve_cholesky_kernel(const double* __restrict__ S, int d, double alpha, int fit
   tc0 = clock64();
   const bool singular = misc[2] != 0.0;
   if (!singular) {
-    // row d now holds z = L^-1 r.  backward: L^T b = z, blocked from the bottom
+    // row d now holds w = D^-1 M^-1 r.  backward: M^T b = w (unit diagonal), blocked from the bottom
     for (int kb = ((d - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
       const int nb = (d - kb) < kNB ? (d - kb) : kNB;
       if (warp == 0) {
-        if (nb == kNB) {
-          const int col = lane & (kNB - 1);
-          double lt[kNB];                                // lt[k] = L[kb+k][kb+col]
+        const int col = lane & (kNB - 1);
+        const bool act = lane < nb;
+        double lt[kNB];                                // lt[k] = M[kb+k][kb+col], k > col
 #pragma unroll
-          for (int k = 0; k < kNB; ++k) lt[k] = lane < kNB ? A[(kb + k) * pitch + kb + col] : 0.0;
-          double z = lane < kNB ? r[kb + col] : 0.0;
-          const double dinv = lane < kNB ? invd[kb + col] : 0.0;
+        for (int k = 0; k < kNB; ++k) lt[k] = (act && k < nb && k > col) ? A[(kb + k) * pitch + kb + col] : 0.0;
+        double z = act ? r[kb + col] : 0.0;
 #pragma unroll
-          for (int k = kNB - 1; k >= 0; --k) {
-            const double bk = __shfl_sync(0xffffffffu, z * dinv, k);
-            z = (lane == k) ? bk : ((lane < k) ? fma(-lt[k], bk, z) : z);   // lanes > k are already final
-          }
-          __syncwarp();
-          if (lane < kNB) r[kb + lane] = z;
-        } else {
-          for (int k = nb - 1; k >= 0; --k) {
-            if (lane == k) r[kb + k] *= invd[kb + k];
-            __syncwarp();
-            if (lane < k) r[kb + lane] -= A[(kb + k) * pitch + kb + lane] * r[kb + k];
-            __syncwarp();
+        for (int k = kNB - 1; k >= 0; --k) {
+          if (k < nb) {
+            const double bk = __shfl_sync(0xffffffffu, z, k);   // lane k is final: every i > k has been subtracted
+            z = (lane < k) ? fma(-lt[k], bk, z) : z;
           }
         }
+        __syncwarp();
+        if (act) r[kb + lane] = z;
       }
       __syncthreads();
       for (int i = tid; i < kb; i += blockDim.x) {
@@ -400,36 +407,220 @@ solve_spectral_kernel(const double* __restrict__ S, int d, double cond, int fit_
   }
 }
 
-size_t solve_smem_bytes(int d) { return sizeof(double) * ((size_t)(d + 1) * (d + 1) + 3 * d + 8); }
+// ---- eigenvalues only: singular_ and rank_ of the fitted estimator -------------------------------------------------
+// LinearRegression.fit stores `singular_` (singular values of the centred X, descending) and `rank_` next to the
+// coefficients (sklearn/linear_model/_base.py: `self.coef_, _, self.rank_, self.singular_ = linalg.lstsq(...)`), and the
+// joblib artefact of stage_1_train_model.py:113-114 carries them.  They are sqrt(eig(Xc^T Xc)), i.e. eigenvalues of the
+// same centred Gram matrix the Cholesky solve factors -- no eigenvectors are needed unless the matrix is rank deficient
+// (then solve_spectral_kernel computes the minimum-norm coefficients).  One CTA:
+//   (a) Householder tridiagonalisation T = Q^T A Q in shared memory (d - 2 reflections; matvec + rank-2 update by all
+//       threads, 3 block syncs per reflection);
+//   (b) eigenvalues of T by multisection on Sturm counts: 4 threads per eigenvalue evaluate the division-free
+//       characteristic-polynomial recurrence (one dependent FMA per row, power-of-two rescaling every 8 rows) at the 4
+//       interior points of its bracket, so every round shrinks every bracket 5x with no block-level synchronisation.
+constexpr int kEigThreads = 512;
+
+__device__ __forceinline__ int sturm_count(const double* __restrict__ dd, const double* __restrict__ ee2, int d, double x) {
+  // number of eigenvalues of T below x = sign changes of p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e_{i-2}^2 p_{i-2}
+  double pm = 1.0, p = dd[0] - x;
+  int count = p < 0.0 ? 1 : 0;
+  if (p == 0.0) { p = -1e-300; count = 1; }
+  for (int i = 1; i < d; ++i) {
+    double pn = fma(dd[i] - x, p, -(ee2[i - 1] * pm));
+    if (pn == 0.0) pn = (p < 0.0) ? 1e-300 : -1e-300;               // a zero counts as a sign change
+    count += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+    pm = p; p = pn;
+    if ((i & 7) == 7) {                                              // keep the pair in range: scale both by 2^-exponent(p)
+      const int eb = (__double2hiint(p) >> 20) & 0x7ff;
+      int sh = 1023 - eb;
+      sh = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+      const double sc = __hiloint2double((1023 + sh) << 20, 0);
+      p *= sc; pm *= sc;
+    }
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(kEigThreads, 1)
+solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const int pitch = d + 1;
+  double* A = sm;                         // symmetric, full storage (both triangles kept current)
+  double* r = A + d * pitch;              // (unused here; build_normal_equations fills it)
+  double* mean = A + (d + 1) * pitch;
+  double* misc = mean + 2 * d;
+  double* v = misc + 8;                   // Householder vector (v[k+1] = 1)
+  double* pv = v + d;                     // tau * A v
+  double* dd = pv + d;                    // diagonal of T
+  double* ee2 = dd + d;                   // squared off-diagonal of T
+  double* lam = ee2 + d;                  // eigenvalues, ascending
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  build_normal_equations(S, d, 0.0, fit_intercept, A, r, mean, &misc[0]);
+
+  for (int k = 0; k + 2 < d; ++k) {
+    const int m = d - k - 1;              // length of the column below the diagonal: rows k+1 .. d-1
+    // (a1) reflection: x = A[k+1.., k] (read as the row k, A is symmetric); beta = -sign(x0) |x|, tau = (beta - x0) / beta
+    if (warp == 0) {
+      double s2 = 0.0;
+      for (int i = lane + 1; i < m; i += 32) { const double x = A[k * pitch + k + 1 + i]; s2 = fma(x, x, s2); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      const double x0 = A[k * pitch + k + 1];
+      double tau = 0.0, beta = x0, scale = 0.0;
+      if (s2 > 0.0) {
+        const double nrm = sqrt(fma(x0, x0, s2));
+        beta = x0 >= 0.0 ? -nrm : nrm;
+        tau = (beta - x0) / beta;
+        scale = 1.0 / (x0 - beta);
+      }
+      for (int i = lane; i < m; i += 32) v[k + 1 + i] = (i == 0) ? 1.0 : A[k * pitch + k + 1 + i] * scale;
+      if (lane == 0) { misc[1] = tau; dd[k] = A[k * pitch + k]; ee2[k] = beta * beta; }
+    }
+    __syncthreads();
+    const double tau = misc[1];
+    if (tau != 0.0) {                     // block-uniform
+      // (a2) p = tau * A22 v: 4 threads per row
+      {
+        const int row = tid >> 2, q = tid & 3;
+        double acc = 0.0;
+        if (row < m) {
+          const double* ar = A + (k + 1 + row) * pitch + k + 1;
+          for (int j = q; j < m; j += 4) acc = fma(ar[j], v[k + 1 + j], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (row < m && q == 0) pv[k + 1 + row] = tau * acc;
+      }
+      __syncthreads();
+      // (a3) K = -tau/2 (p . v), w = p + K v (every warp recomputes K: no extra sync); A22 -= v w^T + w v^T
+      double dot = 0.0;
+      for (int i = lane; i < m; i += 32) dot = fma(pv[k + 1 + i], v[k + 1 + i], dot);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const double K = -0.5 * tau * dot;
+      {
+        const int row = tid >> 2, q = tid & 3;
+        if (row < m) {
+          const double vi = v[k + 1 + row], wi = fma(K, vi, pv[k + 1 + row]);
+          double* ar = A + (k + 1 + row) * pitch + k + 1;
+          for (int j = q; j < m; j += 4) {
+            const double vj = v[k + 1 + j], wj = fma(K, vj, pv[k + 1 + j]);
+            ar[j] -= fma(vi, wj, wi * vj);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (d >= 2) { dd[d - 2] = A[(d - 2) * pitch + d - 2]; ee2[d - 2] = A[(d - 1) * pitch + d - 2] * A[(d - 1) * pitch + d - 2]; }
+    dd[d - 1] = A[(d - 1) * pitch + d - 1];
+    // Gershgorin interval, then a power-of-two scaling so that |d_i - x| <= 2 and e_i^2 <= 1 in the recurrence
+    double glo = dd[0], ghi = dd[0];
+    for (int i = 0; i < d; ++i) {
+      const double rad = (i > 0 ? sqrt(ee2[i - 1]) : 0.0) + (i + 1 < d ? sqrt(ee2[i]) : 0.0);
+      glo = fmin(glo, dd[i] - rad); ghi = fmax(ghi, dd[i] + rad);
+    }
+    const double span = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
+    int ex = ((__double2hiint(span) >> 20) & 0x7ff) - 1023 + 1;
+    ex = ex > 1000 ? 1000 : (ex < -1000 ? -1000 : ex);
+    misc[2] = __hiloint2double((1023 - ex) << 20, 0);   // 2^-ex
+    misc[3] = __hiloint2double((1023 + ex) << 20, 0);   // 2^ex
+    misc[4] = glo; misc[5] = ghi;
+  }
+  __syncthreads();
+  const double sdown = misc[2], sup = misc[3];
+  for (int i = tid; i < d; i += blockDim.x) { dd[i] *= sdown; if (i + 1 < d) ee2[i] *= sdown * sdown; }
+  __syncthreads();
+  // (b) multisection: quad (4 consecutive lanes) owns eigenvalue index e; bracket invariant count(lo) <= e < count(hi)
+  for (int e0 = 0; e0 < d; e0 += kEigThreads / 4) {
+    const int e = e0 + (tid >> 2), q = tid & 3;
+    const bool live = e < d;
+    double lo = misc[4] * sdown, hi = misc[5] * sdown;
+    const double w0 = hi - lo;
+    lo -= 1e-3 * w0 + 1e-300; hi += 1e-3 * w0 + 1e-300;
+    for (int round = 0; round < 26; ++round) {
+      const double step = (hi - lo) * 0.2;
+      const double x = lo + step * (double)(q + 1);
+      const int c = live ? sturm_count(dd, ee2, d, x) : 0;
+      const bool below = c <= e;                       // x is still a lower bound of eigenvalue e
+      // the 4 points are increasing in q: new lo = the last `below` point, new hi = the first non-`below` point
+      const unsigned int quad_shift = (unsigned int)(lane & ~3);
+      const unsigned int bal = (__ballot_sync(0xffffffffu, below) >> quad_shift) & 0xFu;
+      const int nb = __popc(bal);                      // below is monotone in x: the first nb points are lower bounds
+      const double nlo = nb > 0 ? lo + step * (double)nb : lo;
+      const double nhi = nb < 4 ? lo + step * (double)(nb + 1) : hi;
+      lo = nlo; hi = nhi;
+    }
+    if (live && q == 0) lam[e] = 0.5 * (lo + hi) * sup;
+  }
+  __syncthreads();
+  // singular values descending, rank = #{s > cond * s_max}
+  const double lmax = fmax(lam[d - 1], 0.0);
+  const double smax = sqrt(lmax);
+  int rk = 0;
+  for (int i = tid; i < d; i += blockDim.x) {
+    const double sv = sqrt(fmax(lam[d - 1 - i], 0.0));
+    out[kOutSingular + i] = sv;
+    rk += (sv > cond * smax) ? 1 : 0;
+  }
+  __shared__ int rank_total;
+  if (tid == 0) rank_total = 0;
+  __syncthreads();
+  if (rk) atomicAdd(&rank_total, rk);
+  __syncthreads();
+  if (tid == 0) {
+    out[kOutRank] = (double)rank_total;
+    out[kOutInfo] = 0.0;
+    out[kOutRows] = S[d * (d + 2) + d];        // rows in the statistic: singular_ has min(rows, d) entries
+  }
+}
+
+size_t solve_smem_bytes(int d) {
+  return sizeof(double) * ((size_t)(d + 1) * (d + 1) + 3 * d + 16 + (size_t)(d + 1) * kUPitch + 8 * d);
+}
+
+int ensure_solve_attrs(b2_ctx* ctx) {
+  if (!ctx->solve_attr_set) {
+    const int bytes = (int)solve_smem_bytes(kMaxD);
+    B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B2_CUDA(cudaFuncSetAttribute(solve_eigvals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->solve_attr_set = true;
+  }
+  return B2_OK;
+}
 
 }  // namespace
 
-int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept) {
-  const size_t smem = solve_smem_bytes(ctx->d);
-  if (!ctx->solve_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)solve_smem_bytes(kMaxD)));
-    B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)solve_smem_bytes(kMaxD)));
-    ctx->solve_attr_set = true;
-  }
-  solve_cholesky_kernel<<<1, kCholThreads, smem, ctx->stream>>>(ctx->S, ctx->d, alpha, fit_intercept,
-                                                                 ctx->solve_out);
+// The Cholesky (LDL^T) kernel writes its result straight into the pinned host mirror (no D2H copy node): the caller
+// synchronises the stream and reads ctx->solve_host.
+int launch_solve_cholesky(b2_ctx* ctx, double alpha, int fit_intercept, unsigned int gather_epoch) {
+  if (int r = ensure_solve_attrs(ctx)) return r;
+  SolveXchg xc;
+  xc.own = gather_epoch != 0 ? ctx->xchg : nullptr;
+  xc.n_ranks = ctx->n_ranks;
+  xc.epoch = gather_epoch;
+  xc.timeout_ns = ctx->xchg_timeout_ns;
+  solve_cholesky_kernel<<<1, kCholThreads, solve_smem_bytes(ctx->d), ctx->stream>>>(ctx->S, ctx->d, alpha, fit_intercept,
+                                                                                    ctx->solve_host, xc);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return B2_OK;
 }
 
 int launch_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept) {
-  const size_t smem = solve_smem_bytes(ctx->d);
-  if (!ctx->solve_attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(solve_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)solve_smem_bytes(kMaxD)));
-    B2_CUDA(cudaFuncSetAttribute(solve_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)solve_smem_bytes(kMaxD)));
-    ctx->solve_attr_set = true;
-  }
-  solve_spectral_kernel<<<1, 512, smem, ctx->stream>>>(ctx->S, ctx->d, cond, fit_intercept, ctx->solve_out);
+  if (int r = ensure_solve_attrs(ctx)) return r;
+  solve_spectral_kernel<<<1, 512, solve_smem_bytes(ctx->d), ctx->stream>>>(ctx->S, ctx->d, cond, fit_intercept, ctx->solve_out);
+  B2_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return B2_OK;
+}
+
+int launch_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept) {
+  if (int r = ensure_solve_attrs(ctx)) return r;
+  solve_eigvals_kernel<<<1, kEigThreads, solve_smem_bytes(ctx->d), ctx->stream>>>(ctx->S, ctx->d, cond, fit_intercept,
+                                                                                  ctx->solve_out);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return B2_OK;

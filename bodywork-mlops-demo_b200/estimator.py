@@ -40,44 +40,56 @@ def _as_f32_matrix(X) -> np.ndarray:
 
 
 class B200LinearRegression:
+    """The statistic S = [X 1 y]^T [X 1 y] of a fit lives in the (shared) context while the fit runs; whatever an
+    estimator needs of it later -- the next ``partial_fit``, a deferred ``singular_`` / ``rank_`` -- is kept per
+    estimator (``_S``) or guarded by the context's serial number, so two estimators on one context never see each
+    other's rows."""
+
     def __init__(self, *, fit_intercept: bool = True, alpha: float = 0.0, tol: float = 1e-6,
                  ctx: Optional[native.Context] = None):
         self.fit_intercept = fit_intercept
         self.alpha = float(alpha)
         self.tol = tol
         self._ctx = ctx
+        self._S: Optional[np.ndarray] = None     # this estimator's statistic (set by partial_fit / deferred attributes)
+        self._serial = -1                        # ctx.serial right after this estimator's last fit
 
     @property
     def ctx(self) -> native.Context:
         return self._ctx if self._ctx is not None else default_context()
 
     # -- fit -------------------------------------------------------------------------------------
-    def _finish_fit(self, d: int, with_spectrum: bool) -> "B200LinearRegression":
-        ctx = self.ctx
-        try:
-            coef, b0 = ctx.solve(alpha=self.alpha, fit_intercept=self.fit_intercept)
-            spectral = None
-        except np.linalg.LinAlgError:
-            # rank deficient and alpha == 0: the minimum-norm solution gelsd would return (device Jacobi)
-            spectral = ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
-            coef, b0 = spectral[0], spectral[1]
+    def _set_solution(self, coef, b0, d: int) -> None:
         if not (np.all(np.isfinite(coef)) and np.isfinite(b0)):
             # sklearn's check_array refuses such input up front; here it shows up in the statistic
             raise ValueError("Input X or y contains NaN, infinity or a value too large for dtype('float32').")
-        if with_spectrum and spectral is None:
-            spectral = ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
         self.coef_ = coef
         self.intercept_ = np.float64(b0 if self.fit_intercept else 0.0)
         self.n_features_in_ = int(d)
-        if spectral is not None:
-            n_rows = int(round(float(ctx.gram_export()[d, d])))
-            self.singular_ = spectral[2][: min(n_rows, d)]
-            self.rank_ = int(spectral[3])
-        return self
+
+    def _spectrum(self, d: int, need_coef: bool):
+        """singular_ / rank_ of the statistic resident in the context (eigenvalues only, b2_solve_eigvals); when the
+        centred Gram is numerically rank deficient (or the factorisation failed) also the minimum-norm coefficients
+        gelsd would return (b2_solve_spectral, device Jacobi)."""
+        ctx = self.ctx
+        sing, rank, rows = ctx.solve_eigvals(cond=self.tol, fit_intercept=self.fit_intercept)
+        self.singular_ = sing[: min(rows, d)]
+        self.rank_ = int(rank)
+        if (need_coef or (rank < min(rows, d) and self.alpha == 0.0)) and d > 0:
+            coef, b0, sing_j, rank_j = ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
+            self.singular_ = sing_j[: min(rows, d)]
+            self.rank_ = int(rank_j)
+            self._set_solution(coef, b0, d)
+
+    def _drop_spectrum(self) -> None:
+        for name in ("singular_", "rank_"):
+            if hasattr(self, name):
+                delattr(self, name)
 
     def fit(self, X, y, row_mask=None, mask_keep: int = 1, with_spectrum: bool = True) -> "B200LinearRegression":
         """X: (n, D) host array (any float dtype; staged as fp32) or a ``DeviceArray`` (f32 / bf16).
-        ``row_mask`` (uint8 per row) restricts the fit to rows equal to ``mask_keep``."""
+        ``row_mask`` (uint8 per row) restricts the fit to rows equal to ``mask_keep``.
+        ``with_spectrum=False`` defers ``singular_`` / ``rank_`` (computed on first use, e.g. by ``to_sklearn``)."""
         ctx = self.ctx
         if isinstance(X, native.DeviceArray):
             d = X.shape[1]
@@ -88,22 +100,71 @@ class B200LinearRegression:
                 raise ValueError(f"Found input variables with inconsistent numbers of samples: "
                                  f"[{X.shape[0]}, {y.shape[0]}]")
             d = X.shape[1]
-        ctx.gram_reset(d)
-        ctx.gram_accumulate(X, y, row_mask, mask_keep)
-        ctx.gram_allreduce()  # no-op without a communicator
-        return self._finish_fit(d, with_spectrum)
+        self._S = None
+        self._drop_spectrum()
+        singular = False
+        try:
+            coef, b0 = ctx.fit(X, y, row_mask, mask_keep, alpha=self.alpha, fit_intercept=self.fit_intercept)
+            self._set_solution(coef, b0, d)
+        except np.linalg.LinAlgError:
+            singular = True         # rank deficient and alpha == 0: the minimum-norm solution gelsd would return
+        self._serial = ctx.serial
+        if with_spectrum or singular:
+            self._spectrum(d, need_coef=singular)
+        return self
 
     def partial_fit(self, X, y, with_spectrum: bool = False) -> "B200LinearRegression":
-        """Fold one more tranche into the running statistic and re-solve (incremental daily refit)."""
+        """Fold one more tranche into THIS estimator's running statistic and re-solve (incremental daily refit)."""
         ctx = self.ctx
         Xh = X if isinstance(X, native.DeviceArray) else _as_f32_matrix(X)
         d = Xh.shape[1]
-        if ctx.d != d:
-            ctx.gram_reset(d)
         if not isinstance(Xh, native.DeviceArray):
             y = np.ascontiguousarray(np.asarray(y).ravel(), dtype=np.float32)
+        if self._S is not None and self._S.shape[0] == d + 2:
+            ctx.gram_import(self._S)
+        elif hasattr(self, "coef_") and self._serial == ctx.serial and ctx.d == d:
+            pass                       # the statistic of this estimator's last fit is still resident
+        else:
+            ctx.gram_reset(d)          # first tranche of this estimator
         ctx.gram_accumulate(Xh, y)
-        return self._finish_fit(d, with_spectrum)
+        self._drop_spectrum()
+        singular = False
+        try:
+            coef, b0 = ctx.solve(alpha=self.alpha, fit_intercept=self.fit_intercept)
+            self._set_solution(coef, b0, d)
+        except np.linalg.LinAlgError:
+            singular = True
+        self._S = ctx.gram_export()
+        self._serial = ctx.serial
+        if with_spectrum or singular:
+            self._spectrum(d, need_coef=singular)
+        return self
+
+    def solve_resident(self, d: int, S: Optional[np.ndarray] = None) -> "B200LinearRegression":
+        """Solve from the statistic currently resident in the context (after gram_import / gram_accumulate calls made
+        by the caller, e.g. IncrementalTrainer); ``S``: the caller's host copy of it, kept for deferred attributes."""
+        ctx = self.ctx
+        self._drop_spectrum()
+        self._S = S
+        try:
+            coef, b0 = ctx.solve(alpha=self.alpha, fit_intercept=self.fit_intercept)
+            self._set_solution(coef, b0, d)
+        except np.linalg.LinAlgError:
+            self._spectrum(d, need_coef=True)
+        self._serial = ctx.serial
+        return self
+
+    def _ensure_spectrum(self) -> None:
+        if hasattr(self, "rank_"):
+            return
+        ctx = self.ctx
+        if self._S is not None:
+            ctx.gram_import(self._S)
+        elif self._serial != ctx.serial:
+            raise RuntimeError("singular_ / rank_ were deferred (with_spectrum=False) and the statistic of this fit is no "
+                               "longer resident in the context: refit, or fit with with_spectrum=True")
+        self._spectrum(self.n_features_in_, need_coef=False)
+        self._serial = ctx.serial
 
     # -- predict -------------------------------------------------------------------------------------
     def predict(self, X):
@@ -123,11 +184,7 @@ class B200LinearRegression:
         """A real sklearn LinearRegression with the attributes ``fit`` would have set
         (the joblib layout stage_1_train_model.py:113-114 dumps and stage_2_serve_model.py:65 loads)."""
         from sklearn.linear_model import LinearRegression
-        if not hasattr(self, "rank_"):
-            spectral = self.ctx.solve_spectral(cond=self.tol, fit_intercept=self.fit_intercept)
-            n_rows = int(round(float(self.ctx.gram_export()[self.n_features_in_, self.n_features_in_])))
-            self.singular_ = spectral[2][: min(n_rows, self.n_features_in_)]
-            self.rank_ = int(spectral[3])
+        self._ensure_spectrum()
         reg = LinearRegression(fit_intercept=self.fit_intercept)
         reg.coef_ = np.asarray(self.coef_, dtype=np.float64).copy()
         reg.intercept_ = np.float64(self.intercept_)

@@ -96,7 +96,7 @@ class IncrementalTrainer:
                 ctx.gram_reset(self.d)
                 ctx.gram_accumulate(allX, ally, mask, 1)      # host rows: streamed
             self.S = ctx.gram_export()
-            self.model = B200LinearRegression(ctx=ctx)._finish_fit(self.d, with_spectrum=False)
+            self.model = B200LinearRegression(ctx=ctx).solve_resident(self.d, self.S)
         finally:
             Xd.free(); yd.free()
         self.days += 1

@@ -102,7 +102,7 @@ def split_mask(n: int, test_size: float = 0.2, seed: int = 42) -> np.ndarray:
     ``train_test_split(X, y, test_size=0.2, random_state=42)`` (stage_1_train_model.py:98-103) draws:
     ``perm = RandomState(seed).permutation(n)``; test = first ceil(test_size*n), train = next floor((1-test_size)*n)."""
     n_test = int(np.ceil(test_size * n))
-    n_train = int(np.floor((1.0 - test_size) * n))
+    n_train = n - n_test            # sklearn/model_selection/_split.py: the complement when train_size is None
     if n_train < 1 or n_test < 1:
         raise ValueError(f"With n_samples={n}, test_size={test_size}, the resulting train set will be empty.")
     perm = np.random.RandomState(seed).permutation(n)
@@ -136,19 +136,19 @@ def _metrics_record(mape: float, r_squared: float, max_residual: float) -> pd.Da
 def model_metrics(y_actual, y_predicted) -> pd.DataFrame:
     """Regression metrics record (stage_1_train_model.py:79-90), reduced on the GPU.
 
-    Scoring a one-column 'X = y_predicted' with coefficient 1 and intercept 0 reuses the fused
-    predict+metrics kernel, so the three reductions run in fp64 on the device."""
-    ctx = default_context()
-    y = np.ascontiguousarray(np.asarray(y_actual, dtype=np.float64).ravel(), dtype=np.float32)
-    p = np.ascontiguousarray(np.asarray(y_predicted, dtype=np.float64).reshape(-1, 1), dtype=np.float32)
-    _, stats = ctx.score(p, np.ones(1), 0.0, y=y, want_yhat=False)
+    The two vectors go to ``b2_metrics`` in float64 (the reference computes on float64 arrays), so MAPE, r_squared
+    and max_residual agree with scikit-learn's to rounding; float32 inputs stay float32."""
+    stats = default_context().metrics(y_actual, y_predicted)
     return _metrics_record(*metrics_from_stats(stats))
 
 
 def train_model(data: pd.DataFrame):
     """Train the regression model and compute hold-out metrics (stage_1_train_model.py:93-108).
 
-    Returns ``(sklearn LinearRegression, one-row metrics DataFrame)`` like the reference."""
+    Returns ``(sklearn LinearRegression, one-row metrics DataFrame)`` like the reference.
+    Numeric contract: the rows are staged as float32 (what the kernels stream; the reference keeps pandas' float64),
+    sums, solve, predictions and metric reductions are float64 -- coefficients agree with the reference's to ~1e-6
+    relative, metrics to ~1e-7 (asserted against fixtures produced by the unmodified reference)."""
     cols = feature_columns(data)
     X = np.ascontiguousarray(data[cols].to_numpy(dtype=np.float32))
     y = np.ascontiguousarray(data["y"].to_numpy(dtype=np.float32))

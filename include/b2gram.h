@@ -30,12 +30,13 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 #define B2_MAX_D 128
 
 /* element type of X */
 #define B2_F32 0
 #define B2_BF16 1
+#define B2_F64 2 /* b2_metrics only */
 
 /* where a caller buffer lives */
 #define B2_MEM_DEVICE 0 /* device pointer (HBM)                                   */
@@ -62,7 +63,8 @@ extern "C" {
 #define B2_E_CUDA (-2)
 #define B2_E_STATE (-3)
 #define B2_E_SINGULAR (-4) /* Cholesky met a non-positive pivot (rank-deficient, alpha == 0) */
-#define B2_E_NCCL (-5)
+#define B2_E_COMM (-5) /* NCCL failure, or a peer did not deliver its partial statistic within the timeout */
+#define B2_E_NCCL B2_E_COMM
 #define B2_E_UNSUPPORTED (-6)
 
 typedef struct b2_ctx b2_ctx;
@@ -110,16 +112,32 @@ int b2_gram_allreduce(b2_ctx* ctx);
 int b2_gram_export(b2_ctx* ctx, double* S_out, int64_t* n_rows_out);
 int b2_gram_import(b2_ctx* ctx, const double* S_in, int d);
 
+/* ---- the whole fit in one call: LinearRegression(fit_intercept).fit(X, y) / Ridge(alpha) ----------------------
+ * reference: stage_1_train_model.py:105-106.  Equivalent to b2_gram_reset + b2_gram_accumulate + b2_gram_allreduce +
+ * b2_solve with the same arguments.  Device-resident rows that take the tensor-core kernel run as two launches: the
+ * Gram kernel (reduces and folds its own partials, stores S into the peers' exchange slots when a peer exchange is
+ * attached) and the solve kernel (sums the peers' slots, factors, writes coef / intercept to the host). */
+int b2_fit(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_rows, int d, int64_t ldx,
+           int mem_kind, const uint8_t* row_mask, int mask_keep, double alpha, int fit_intercept,
+           double* coef, double* intercept);
+
 /* ---- solve: replaces scipy.linalg.lstsq + _set_intercept ----------------------------------------
  * reference: sklearn/linear_model/_base.py (lstsq on centred data; intercept_ = y_mean - x_mean.coef_)
- * Single-SM fp64 Cholesky of (Xc^T Xc + alpha I).  coef: d doubles, intercept: 1 double (host).
- * fit_intercept = 0 solves the uncentred problem.  Returns B2_E_SINGULAR on a non-positive pivot. */
+ * Single-SM fp64 LDL^T (square-root-free Cholesky) of (Xc^T Xc + alpha I).  coef: d doubles, intercept: 1 double
+ * (host).  fit_intercept = 0 solves the uncentred problem.  Returns B2_E_SINGULAR on a non-positive pivot and
+ * B2_E_COMM when the preceding peer-memory exchange timed out (S incomplete). */
 int b2_solve(b2_ctx* ctx, double alpha, int fit_intercept, double* coef, double* intercept);
 /* eigenvalues of the centred Gram (device Jacobi) -> singular_ (descending, d doubles) and rank_
  * (count of singular values > cond * max), plus the minimum-norm coefficients gelsd would return.
  * Any output pointer may be NULL. */
 int b2_solve_spectral(b2_ctx* ctx, double cond, int fit_intercept, double* coef, double* intercept,
                       double* singular, int* rank);
+
+/* singular_ (descending, d doubles) and rank_ only -- the attributes LinearRegression.fit stores beside coef_
+ * (sklearn/linear_model/_base.py) -- as sqrt of the eigenvalues of the centred Gram: Householder tridiagonalisation +
+ * Sturm multisection on one SM, no eigenvectors (b2_solve_spectral is only needed when rank < d). */
+int b2_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept, double* singular, int* rank,
+                     int64_t* n_rows_out /* rows in S; may be NULL */);
 
 /* ---- scoring: replaces model.predict and model_metrics ------------------------------------------
  * reference: stage_1_train_model.py:107 / stage_2_serve_model.py:78 (X @ coef_ + intercept_)
@@ -135,12 +153,23 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
              int mem_kind, const double* coef, double intercept, const float* y,
              const uint8_t* row_mask, int mask_keep, float* yhat, double* stats_out);
 int b2_score_allreduce(b2_ctx* ctx, double* stats_inout);
+/* model_metrics(y_actual, y_predicted) (stage_1_train_model.py:79-90) on two vectors of dtype B2_F32 or B2_F64
+ * (the reference works on float64 arrays): the same ten reductions as b2_score, divisions correctly rounded. */
+int b2_metrics(b2_ctx* ctx, const void* y_actual, const void* y_predicted, int dtype, int64_t n_rows,
+               int mem_kind, double* stats_out);
 
 /* ---- synthetic rows on the device (benchmarks): stage_3_synthetic_data_generation.py:36-43 --------
  * X_ij ~ U(0,100), eps ~ N(0,1), y = alpha + beta * sum_j X_ij + sigma * eps   (Philox4x32-10,
  * counter = global row index + row_offset, so shards of one dataset can be drawn independently). */
 int b2_synth(b2_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n_rows, int d, int64_t ldx,
              int x_dtype, double alpha, double beta, double sigma, void* X_dev, float* y_dev);
+
+/* One reference tranche (D = 1) of day `day` >= 1, exactly as generate_dataset draws it
+ * (stage_3_synthetic_data_generation.py:28-43): alpha(day) = 1 + 0.5 sin(2 pi 6 (day - 1) / 364), X ~ U(0,100),
+ * y = alpha + beta X + sigma eps, rows with y < 0 dropped, order kept.  X_dev / y_dev hold n_rows floats; the
+ * number of rows written comes back in *n_kept_out. */
+int b2_synth_tranche(b2_ctx* ctx, uint64_t seed, int64_t n_rows, int day, double beta, double sigma,
+                     float* X_dev, float* y_dev, int64_t* n_kept_out);
 
 /* ---- multi-GPU (one process per GPU; NCCL is dlopen'ed on first use) ------------------------------ */
 int b2_comm_unique_id(char* id_out /* 128 bytes */);
@@ -154,6 +183,16 @@ int b2_comm_barrier(b2_ctx* ctx);
 int b2_comm_p2p_export(b2_ctx* ctx, char* handle_out /* 64 bytes */);
 int b2_comm_p2p_attach(b2_ctx* ctx, int n_ranks, int rank, const char* handles /* n_ranks x 64 bytes */);
 int b2_comm_p2p_detach(b2_ctx* ctx); /* back to the NCCL all-reduce (all ranks must detach together) */
+/* the same exchange between contexts of ONE process (several GPUs driven by one C client, or two contexts on one
+ * GPU): peers[r] is rank r's context, peers[rank] == ctx.  Every context of the group calls it once. */
+int b2_comm_p2p_attach_local(b2_ctx* ctx, int n_ranks, int rank, b2_ctx* const* peers);
+/* how long a rank waits for a peer's partial statistic before the exchange fails with B2_E_COMM (default 10 000 ms) */
+int b2_comm_set_timeout_ms(b2_ctx* ctx, int64_t ms);
+/* ranks, this rank, and which exchange b2_gram_allreduce / b2_fit use (B2_EXCHANGE_*) */
+#define B2_EXCHANGE_NONE 0
+#define B2_EXCHANGE_NCCL 1
+#define B2_EXCHANGE_PEER 2
+int b2_comm_info(b2_ctx* ctx, int* n_ranks_out, int* rank_out, int* exchange_out);
 
 /* ---- timing (CUDA events on the ctx stream) ---------------------------------------------------------
  * b2_timer_start/stop bracket any sequence of calls; *_ms is device time between the two events.
@@ -164,6 +203,8 @@ int b2_timer_stop(b2_ctx* ctx, double* ms_out);
 int b2_last_kernel_ms(b2_ctx* ctx, double* gram_ms_out, int* launches_out);
 /* total number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int b2_launch_count(b2_ctx* ctx, int64_t* n_out);
+/* out3[0] fits that took the fused two-launch path of b2_fit, [1] peer exchanges started, [2] kernels launched */
+int b2_ctx_stats(b2_ctx* ctx, int64_t* out3);
 
 #ifdef __cplusplus
 }

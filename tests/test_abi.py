@@ -80,7 +80,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
 
 def test_abi_version_and_error_string():
     lib = b2.native.load()
-    assert lib.b2_abi_version() == 1
+    assert lib.b2_abi_version() == 2
     assert isinstance(b2.native.last_error(), str)
 
 
