@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- train rows/sec of the N x 128 least-squares fit (BASELINE.json `metric`).
 
-One "step" = one complete fit of the resident rows through the C-ABI:
-    b2_gram_reset -> b2_gram_accumulate (tcgen05 Gram kernel over every row of this rank's shard)
-    -> b2_gram_allreduce (NCCL, N > 1 only) -> b2_solve (single-SM Cholesky, coefficients to the host)
+One "step" = one complete fit of the resident rows through the C-ABI (b2_fit): four kernel launches --
+    tc_shift_kernel     per-column shift from a 2048-row sample
+    gram_tc_kernel      tcgen05 Gram over every row of this rank's shard (the roofline kernel)
+    tc_finalize_kernel  reduce the per-CTA partials, fold into S, store S into every peer's exchange slot over NVLink (N > 1)
+    solve kernel        waits for the peers' slots and sums them (N > 1), LDL^T, coefficients written to pinned host memory
 
 Arms
     python bench.py [--gpus N --steps K --warmup W]          this repo (one process per GPU under torchrun)
@@ -11,7 +13,11 @@ Arms
                                                              LinearRegression.fit (stage_1_train_model.py:105-106)
                                                              on a bounded sample, all host threads, rank 0 only
 
-Keys of the JSON line follow the driver's contract; see DESIGN.md "Measurement".
+Every N runs the SAME per-GPU shard (12.5 M x 128: BASELINE configs[2] over 8 GPUs), carries `parity` (the headline
+fit against the exact fp64 kernel over the same full-size rows and the same exchange, S bit-identical across ranks) and
+`exchange` (which exchange actually ran).  N = 1 adds `north_star` (100 M x 128 on one GPU), `config1_10Mx128`,
+`companion_score`, `cpu_baseline`; N > 1 adds `strong_100M` and `score_shard`.  Keys follow the driver's contract; see
+DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -29,8 +35,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D = 128
-ROWS_N1 = 10_000_000       # BASELINE.json configs[1]
-ROWS_PER_GPU_MULTI = 12_500_000  # BASELINE.json configs[2]: 100 M rows over 8 GPUs
+ROWS_CONFIG1 = 10_000_000      # BASELINE.json configs[1]
+ROWS_PER_GPU = 12_500_000      # BASELINE.json configs[2]: 100 M rows over 8 GPUs -- the shard of every N (same-shard scaling)
+NORTH_STAR_ROWS = 100_000_000  # BASELINE.json north_star: 100 M x 128 on one GPU
 METRIC = "train rows/sec (N x 128 least-squares fit)"
 UNIT = "rows/s"
 
@@ -200,14 +207,66 @@ def run_reference(args) -> None:
     }))
 
 
-def workload_config(n_gpus: int, x_kind: str) -> dict:
-    rows = ROWS_N1 if n_gpus == 1 else ROWS_PER_GPU_MULTI
+def workload_config(n_gpus: int, x_kind: str, rows: int = 0) -> dict:
+    rows = rows or ROWS_PER_GPU
     return {"workload": (f"{rows * n_gpus} rows x {D} features ({rows} per GPU, row-sharded), X {x_kind} + y fp32 "
-                         f"resident in HBM; BASELINE.json configs[{1 if n_gpus == 1 else 2}]"),
+                         f"resident in HBM; the per-GPU shard of BASELINE.json configs[2] (100 M x 128 over 8 GPUs) at "
+                         f"every N, so the driver's efficiency is same-shard; configs[1] (10 M x 128) is the "
+                         f"`config1_10Mx128` object of the N = 1 line"),
             "rows_per_gpu": rows, "features": D, "x_storage": x_kind,
-            "parallelism": f"row-shard x{n_gpus}, one all-reduce of the (D+2)^2 fp64 statistic per fit (peer-memory one-shot "
-                           f"exchange over NVLink; NCCL all-reduce when B2_NO_P2P=1)",
-            "l2": "inputs larger than L2 (5.2 GB per pass vs 126 MB)"}
+            "parallelism": f"row-shard x{n_gpus}, one exchange of the (D+2)^2 fp64 statistic per fit",
+            "l2": f"inputs larger than L2 ({rows * (D * (4 if x_kind == 'f32' else 2) + 4) / 1e9:.2f} GB per pass vs 126 MB)"}
+
+
+def max_over_ranks(dist, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_fits(ctx, dist, X, y, steps: int, warmup: int, barrier):
+    """`steps` complete fits (b2_fit: Gram + exchange + solve, coefficients on the host), CUDA-event timed, max over
+    ranks.  Returns (ms_total, gram_kernel_ms_avg, launches, last (coef, intercept))."""
+    for _ in range(warmup):
+        sol = ctx.fit(X, y)
+    ctx.last_kernel_ms()
+    l0 = ctx.launch_count()
+    barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        sol = ctx.fit(X, y)
+    ms = ctx.timer_stop()
+    barrier()
+    kms, kl = ctx.last_kernel_ms()
+    return max_over_ranks(dist, ms), kms / max(kl, 1), ctx.launch_count() - l0, sol
+
+
+def exact_check(ctx, b2, X, y, d, sol, dist, tag: str) -> dict:
+    """Oracle check of a full-size fit: the same rows through the exact fp64 CUDA-core kernel (KERNEL_SIMT -- pinned to the
+    numpy oracle at 1e-12 by tests/ and, in this run, by `oracle_pin`), the same exchange, the same solve."""
+    coef, b0 = sol
+    S_head = ctx.gram_export()
+    ctx.set_kernel(b2.KERNEL_SIMT)
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.gram_reset(d); ctx.gram_accumulate(X, y); ctx.gram_allreduce()
+    c_ex, b_ex = ctx.solve()
+    secs = time.perf_counter() - t0
+    S_ex = ctx.gram_export()
+    ctx.set_kernel(b2.KERNEL_TCGEN05)
+    out = {"what": f"{tag}: headline fit vs the exact fp64 kernel over the SAME full-size rows + the same exchange",
+           "coef_linf": float(np.max(np.abs(coef - c_ex))), "intercept_abs_err": float(abs(b0 - b_ex)),
+           "statistic_rel_err": float(np.max(np.abs(S_head - S_ex)) / np.max(np.abs(S_ex))),
+           "rows_in_statistic": float(S_head[d, d]), "exact_kernel_seconds": secs, "tolerance": 1e-4}
+    if dist is not None:
+        import hashlib
+        hs = [None] * dist.get_world_size()
+        dist.all_gather_object(hs, hashlib.sha256(S_head.tobytes() + coef.tobytes()).hexdigest())
+        out["bit_identical_across_ranks"] = bool(all(h == hs[0] for h in hs))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -218,14 +277,17 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--x-dtype", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: BASELINE config)")
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 12.5 M, the configs[2] shard)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip north_star / strong_100M / config1 variants / companion (profiling runs)")
+    ap.add_argument("--no-variants", action="store_true", help="alias of --no-extras")
     ap.add_argument("--precision", default="split", choices=["split", "bf16"],
                     help="tensor-core operand precision: bf16 hi+lo split (default) or a single bf16 operand")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    extras = not (args.no_extras or args.no_variants)
 
     if args.impl == "reference":
         run_reference(args)
@@ -243,13 +305,13 @@ def main() -> None:
 
     dist = None
     if world > 1:
-        import torch
+        import torch  # noqa: F401
         import torch.distributed as dist  # rendezvous / barrier / max-over-ranks only (gloo, CPU tensors)
         dist.init_process_group("gloo", init_method="env://", rank=rank, world_size=world)
 
     ctx = b2.Context(local_rank)
+    exchange_note = None
     if world > 1:
-        import torch
         uid = [b2.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         # NCCL may print its version banner on stdout; stdout carries exactly one JSON line, so park fd 1 on stderr
@@ -263,11 +325,11 @@ def main() -> None:
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
         if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
-            # one-shot peer-memory exchange of S (NVLink stores + flags) instead of an NCCL launch per step
+            # one-shot peer-memory exchange of S (NVLink stores + flags) fused into the Gram / solve kernels
             try:
                 mine = ctx.comm_p2p_export()
             except Exception as exc:   # e.g. CUDA IPC unavailable in this container
-                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc})", file=sys.stderr)
+                exchange_note = f"rank {rank}: peer-memory export failed ({exc})"
                 mine = None
             handles = [None] * world
             dist.all_gather_object(handles, mine)          # every rank takes part in both collectives
@@ -276,35 +338,39 @@ def main() -> None:
                 try:
                     ctx.comm_p2p_attach(world, rank, handles)
                 except Exception as exc:
-                    print(f"[bench] rank {rank}: attaching peer buffers failed ({exc}); using NCCL", file=sys.stderr)
+                    exchange_note = f"rank {rank}: attaching peer buffers failed ({exc})"
                     ok = False
             oks = [None] * world
-            dist.all_gather_object(oks, ok)
+            dist.all_gather_object(oks, ok)                # also the barrier between attach and the first exchange
             if not all(oks):
                 ctx.comm_p2p_detach()
-
-    rows = args.rows or (ROWS_N1 if world == 1 else ROWS_PER_GPU_MULTI)
-    kind = args.x_dtype
-    X, y = ctx.synth(rows, D, seed=1234, row_offset=rank * rows, kind=kind)
-    ctx.set_kernel(b2.KERNEL_TCGEN05)
-    ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
-    ctx.sync()
-
-    def step():
-        ctx.gram_reset(D)
-        ctx.gram_accumulate(X, y)
-        ctx.gram_allreduce()
-        return ctx.solve()
+                exchange_note = (exchange_note or "a peer could not attach") + "; NCCL all-reduce used"
+        else:
+            exchange_note = "B2_NO_P2P=1: NCCL all-reduce"
+        if exchange_note:
+            print(f"[bench] {exchange_note}", file=sys.stderr)
 
     def barrier():
         ctx.sync()
         if dist is not None:
             dist.barrier()
 
+    rows = args.rows or ROWS_PER_GPU
+    kind = args.x_dtype
+    X, y = ctx.synth(rows, D, seed=1234, row_offset=rank * rows, kind=kind)
+    ctx.set_kernel(b2.KERNEL_TCGEN05)
+    ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
+    ctx.sync()
+    peak, peak_src = measured_peaks()
+    bytes_per_row = D * (4 if kind == "f32" else 2) + 4
+    mma_per_row = 2.0 * 128 * 144 * (2 if args.precision == "split" else 1)
+
+    # ---- headline: `steps` complete fits of the resident shard --------------------------------------------------
     for _ in range(args.warmup):
-        coef, b0 = step()
+        coef, b0 = ctx.fit(X, y)
     ctx.last_kernel_ms()
     launches0 = ctx.launch_count()
+    fused0 = ctx.stats()["fused_fits"]
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -312,95 +378,125 @@ def main() -> None:
     ctx.timer_start()
     t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        coef, b0 = step()
+        coef, b0 = ctx.fit(X, y)
     ms = ctx.timer_stop()
     t_host = time.perf_counter() - t_host0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     kernel_ms, kernel_launches = ctx.last_kernel_ms()
     launches = ctx.launch_count() - launches0
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    fused_fits = ctx.stats()["fused_fits"] - fused0
+    ms = max_over_ranks(dist, ms)
 
     total_rows = rows * world
     value = total_rows * args.steps / (ms * 1e-3)
-    bytes_per_row = D * (4 if kind == "f32" else 2) + 4
-    peak, peak_src = measured_peaks()
     gram_ms = kernel_ms / max(kernel_launches, 1)
     achieved = rows * bytes_per_row / (gram_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gram_tc_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "mma_tflops_issued": rows * 2.0 * 128 * 144 * (2 if args.precision == "split" else 1) / gram_ms / 1e9
-                                     if D == 128 else None,
+    roofline = {"bound": "hbm", "kernel": "gram_tc_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "mma_tflops_issued": rows * mma_per_row / gram_ms / 1e9,
                 "algorithmic_bytes_per_row": bytes_per_row, "rows_per_launch": rows,
                 "kernel_ms_avg": gram_ms, "kernel_share_of_step": gram_ms / (ms / args.steps),
+                "step_tail_us": 1e3 * (ms / args.steps - gram_ms),
+                "whole_fit_frac_of_hbm_peak": rows * bytes_per_row / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "traffic": ncu_traffic_per_launch(f"{kind}_{rows}x{D}")}
+    info = ctx.comm_info()
+    exchange = {"exchange_used": info["exchange"], "n_ranks": info["n_ranks"], "note": exchange_note,
+                "fused_fits": fused_fits, "of_steps": args.steps,
+                "launches_per_step": launches / max(args.steps, 1)}
 
-    # ---- e2e: the public estimator API on HOST (pinned) rows; H2D inside the timed region ----------------
+    # ---- parity of the HEADLINE fit at this N: exact kernel over the same rows + the same exchange ------------------
+    parity = exact_check(ctx, b2, X, y, D, (coef, b0), dist, f"{total_rows} x {D}")
+    parity["rows_expected"] = float(total_rows)
+    parity["row_count_exact"] = bool(parity["rows_in_statistic"] == float(total_rows))
+
+    # ---- sharded scoring: b2_score per shard + b2_score_allreduce, checked against the host-side combination ----------
+    score_shard = None
+    if world > 1:
+        ctx.set_kernel(b2.KERNEL_AUTO)
+        _yh, st_local = ctx.score(X, coef, float(b0), y=y, want_yhat=False)
+        st_all = ctx.score_allreduce(st_local.copy())
+        parts = [None] * world
+        dist.all_gather_object(parts, st_local.tolist())
+        want = b2.sharding.combine_score_stats(np.array(parts))
+        score_shard = {"what": "b2_score on every shard + b2_score_allreduce (8 sums + 2 maxima over NCCL) vs the "
+                               "combination of the per-rank statistics gathered over gloo",
+                       "rel_err": float(np.max(np.abs(st_all - want) / np.maximum(np.abs(want), 1e-300))),
+                       "rows": float(st_all[5]),
+                       "r_squared": float(1.0 - st_all[1] / max(st_all[3] - st_all[2] ** 2 / max(st_all[5], 1.0), 1e-300))}
+        ctx.set_kernel(b2.KERNEL_TCGEN05)
+
+    # ---- e2e: the public estimator API with DEFAULT arguments on HOST rows; H2D inside the timed region -------------
     e2e = None
     if not args.no_e2e:
-        e2e_rows = rows
-        Xp = ctx.pinned((e2e_rows, D), np.float32 if kind == "f32" else np.uint16)
-        yp = ctx.pinned((e2e_rows,), np.float32)
+        Xp = ctx.pinned((rows, D), np.float32 if kind == "f32" else np.uint16)
+        yp = ctx.pinned((rows,), np.float32)
         b2.native._check(b2.native.load().b2_copy_d2h(ctx._h, Xp.ptr, X.ptr, X.nbytes), "d2h X")
         b2.native._check(b2.native.load().b2_copy_d2h(ctx._h, yp.ptr, y.ptr, y.nbytes), "d2h y")
         est = b2.B200LinearRegression(ctx=ctx)
         ctx.set_kernel(b2.KERNEL_AUTO)
-        e2e_steps = max(2, min(args.steps, 5))
-        est.fit(Xp.array, yp.array, with_spectrum=False)   # warm-up (allocates the staging ring)
+        e2e_steps = max(2, min(args.steps, 4))
+        est.fit(Xp.array, yp.array)                    # warm-up (allocates the staging ring)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            est.fit(Xp.array, yp.array, with_spectrum=False)
+            est.fit(Xp.array, yp.array)                # default arguments: coefficients AND singular_ / rank_
         dt = time.perf_counter() - t0
         barrier()
-        if dist is not None:
-            import torch
-            t = torch.tensor([dt], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dist, dt)
         e2e = {"value": total_rows * e2e_steps / dt, "unit": UNIT, "steps": e2e_steps,
-               "h2d_bytes_per_step": int(e2e_rows * bytes_per_row), "d2h_bytes_per_step": int((D + 1) * 8 + 8 * 4),
-               "api": "B200LinearRegression.fit(X_host_pinned, y_host_pinned) -> b2_gram_accumulate(B2_MEM_HOST)",
-               "coef_linf_vs_resident": float(np.max(np.abs(est.coef_ - coef)))}
+               "h2d_bytes_per_step": int(rows * bytes_per_row), "d2h_bytes_per_step": int((2 * D + 8) * 8 * 2),
+               "api": "B200LinearRegression().fit(X_host_pinned, y_host_pinned), default arguments (coef_, intercept_, "
+                      "singular_, rank_) -> b2_fit(B2_MEM_HOST) + b2_solve_eigvals",
+               "coef_linf_vs_resident": float(np.max(np.abs(est.coef_ - coef))), "rank_": int(est.rank_)}
+        if world == 1 and extras:
+            # the same call on ordinary (pageable) numpy rows -- what train_model hands over -- and train_model itself
+            m = min(rows, 2_000_000)
+            Xn, yn = np.array(Xp.array[:m]), np.array(yp.array[:m])
+            if kind == "f32":
+                est.fit(Xn, yn)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    est.fit(Xn, yn)
+                e2e["pageable_rows_per_s"] = m * 3 / (time.perf_counter() - t0)
+                e2e["pageable_sample"] = f"{m} x {D} fp32 rows in pageable host memory, default fit()"
+                import pandas as pd
+                from bodywork_mlops_demo_b200 import stage_1_train_model as s1
+                mt = 500_000
+                df = pd.DataFrame(Xn[:mt], columns=[f"X{j}" for j in range(D)])
+                df.insert(0, "y", yn[:mt]); df.insert(0, "date", "2021-01-01")
+                s1.train_model(df)
+                t0 = time.perf_counter()
+                model, metrics = s1.train_model(df)
+                e2e["train_model_rows_per_s"] = mt / (time.perf_counter() - t0)
+                e2e["train_model_sample"] = (f"stage_1 train_model(DataFrame {mt} x {D}): split mask + masked fit + hold-out "
+                                             f"scoring + sklearn artefact; r_squared {float(metrics['r_squared'][0]):.4f}")
+                del df
         Xp.free(); yp.free()
+        ctx.set_kernel(b2.KERNEL_TCGEN05)
 
-    # ---- other operand / storage variants of configs[1] (N = 1 only; kernel + whole-fit rates, same timing rules) --
-    variants = None
-    if world == 1 and not args.no_variants:
-        variants = {}
-        for vk, vprec in ((kind, "bf16"), ("bf16" if kind == "f32" else "f32", "split"),
-                          ("bf16" if kind == "f32" else "f32", "bf16")):
-            Xv, yv = (X, y) if vk == kind else ctx.synth(rows, D, seed=1234, kind=vk)
-            ctx.set_kernel(b2.KERNEL_TCGEN05)
+    # ---- BASELINE configs[1]: 10 M x 128 on one GPU, every storage x operand combination ---------------------------
+    config1 = None
+    if world == 1 and extras:
+        config1 = {"what": "BASELINE.json configs[1]: 10 M x 128 rows resident on one GPU; complete fits (b2_fit)", "rows": ROWS_CONFIG1}
+        for vk, vprec in (("f32", "split"), ("f32", "bf16"), ("bf16", "split"), ("bf16", "bf16")):
+            Xv, yv = ctx.synth(ROWS_CONFIG1, D, seed=1234, kind=vk)
             ctx.set_precision(b2.PRECISION_BF16 if vprec == "bf16" else b2.PRECISION_SPLIT)
-            for _ in range(3):
-                ctx.gram_reset(D); ctx.gram_accumulate(Xv, yv); ctx.solve()
-            ctx.last_kernel_ms()
-            ctx.sync(); ctx.timer_start()
-            for _ in range(10):
-                ctx.gram_reset(D); ctx.gram_accumulate(Xv, yv); cv, _b = ctx.solve()
-            vms = ctx.timer_stop() / 10
-            kms, kl = ctx.last_kernel_ms()
+            vms, vk_ms, _l, vsol = time_fits(ctx, None, Xv, yv, 10, 3, barrier)
             bpr = D * (4 if vk == "f32" else 2) + 4
-            variants[f"x_{vk}_operands_{'bf16x1' if vprec == 'bf16' else 'bf16x2'}"] = {
-                "fit_rows_per_s": rows / vms * 1e3, "gram_kernel_ms": kms / max(kl, 1),
-                "frac_of_hbm_peak": rows * bpr / (kms / max(kl, 1)) / 1e6 / peak,
-                # flops as issued to the MMA: 2 * 128 * 144 per row and operand (hi, and lo in split mode)
-                "mma_tflops_issued": rows * 2.0 * 128 * 144 * (1 if vprec == "bf16" else 2) / (kms / max(kl, 1)) / 1e9,
-                "frac_of_bf16_tensor_peak": rows * 2.0 * 128 * 144 * (1 if vprec == "bf16" else 2) / (kms / max(kl, 1))
-                                            / 1e9 / measured_tensor_peak(),
-                "coef_linf_vs_headline_fit": float(np.max(np.abs(cv - coef)))}
-            ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
-            if vk != kind:
-                Xv.free(); yv.free()
+            mma = 2.0 * 128 * 144 * (1 if vprec == "bf16" else 2)
+            config1[f"x_{vk}_operands_{'bf16x1' if vprec == 'bf16' else 'bf16x2'}"] = {
+                "fit_rows_per_s": ROWS_CONFIG1 / (vms / 10) * 1e3, "ms_per_fit": vms / 10, "gram_kernel_ms": vk_ms,
+                "frac_of_hbm_peak": ROWS_CONFIG1 * bpr / vk_ms / 1e6 / peak,
+                "mma_tflops_issued": ROWS_CONFIG1 * mma / vk_ms / 1e9,
+                "frac_of_bf16_tensor_peak": ROWS_CONFIG1 * mma / vk_ms / 1e9 / measured_tensor_peak(),
+                "coef_head": [float(c) for c in vsol[0][:2]]}
+            Xv.free(); yv.free()
+        ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
 
     # ---- companion kernel: hold-out scoring + metrics over the same resident rows (stage_1...:107, 79-90) ----------
     companion = None
-    if world == 1 and not args.no_variants:
+    if world == 1 and extras:
         ctx.set_kernel(b2.KERNEL_AUTO)
         for _ in range(3):
             ctx.score(X, coef, float(b0), y=y, want_yhat=False)
@@ -408,35 +504,94 @@ def main() -> None:
         for _ in range(10):
             _yh, sstats = ctx.score(X, coef, float(b0), y=y, want_yhat=False)
         sms = ctx.timer_stop() / 10
-        sbpr = D * (4 if kind == "f32" else 2) + 4
         companion = {"what": "b2_score: X.coef + intercept fused with the ten metric reductions, resident rows, no yhat write",
-                     "ms": sms, "rows_per_s": rows / sms * 1e3, "bytes_per_row": sbpr,
-                     "frac_of_hbm_peak": rows * sbpr / sms / 1e6 / peak,
+                     "ms": sms, "rows_per_s": rows / sms * 1e3, "bytes_per_row": bytes_per_row,
+                     "frac_of_hbm_peak": rows * bytes_per_row / sms / 1e6 / peak,
                      "note": "timed with CUDA events around 10 calls; includes the 80-byte D2H of the statistics per call",
                      "r_squared": float(1.0 - sstats[1] / max(sstats[3] - sstats[2] ** 2 / max(sstats[5], 1.0), 1e-300))}
-
-    # ---- CPU baseline: sklearn on the host cores, bounded sample, rank 0 at N = 1 only --------------------
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_rows = 1_000_000
-        v, secs, _ = sklearn_fit_rows_per_s(sample_rows)
-        cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "seconds": secs,
-               "sample": f"{sample_rows} x {D} fp32 rows, one LinearRegression(fit_intercept=True).fit "
-                         f"(stage_1_train_model.py:105-106), all BLAS threads"}
-        # coefficient parity on rows both sides see: first 200k rows of the device buffer
-        from sklearn.linear_model import LinearRegression
-        m = 200_000
-        Xh = X.to_host()[:m]
-        yh = y.to_host()[:m]
-        Xf = Xh.astype(np.float64) if kind == "f32" else b2.native.from_bf16_bits(Xh).astype(np.float64)
-        reg = LinearRegression().fit(Xf, yh.astype(np.float64))
-        sub = b2.B200LinearRegression(ctx=ctx)
         ctx.set_kernel(b2.KERNEL_TCGEN05)
-        Xs, ys = ctx.to_device(Xh, kind), ctx.to_device(yh)
-        sub.fit(Xs, ys, with_spectrum=False)
-        parity = {"rows": m, "coef_linf_vs_sklearn_fp64": float(np.max(np.abs(sub.coef_ - reg.coef_))),
-                  "intercept_abs_err": float(abs(sub.intercept_ - reg.intercept_)), "tolerance": 1e-4}
+
+    # ---- CPU baseline + oracle pin: numpy / sklearn on the host cores, bounded samples, rank 0 ------------------------
+    cpu = None
+    oracle_pin = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:   # torchrun exports OMP_NUM_THREADS=1
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
+        from oracle import ols_oracle as orc
+        from sklearn.linear_model import LinearRegression
+        # (1) the exact kernel IS the numpy oracle: statistic of the first rows of this rank's shard, both ways
+        m = 400_000
+        lib = b2.native.load()
+        es = 4 if kind == "f32" else 2
+        Xh = np.empty((m, D), dtype=np.float32 if kind == "f32" else np.uint16)
+        yh = np.empty(m, dtype=np.float32)
+        b2.native._check(lib.b2_copy_d2h(ctx._h, Xh.ctypes.data, X.ptr, m * D * es), "d2h X head")
+        b2.native._check(lib.b2_copy_d2h(ctx._h, yh.ctypes.data, y.ptr, m * 4), "d2h y head")
+        Xf = Xh.astype(np.float64) if kind == "f32" else b2.native.from_bf16_bits(Xh).astype(np.float64)
+        S_np = orc.gram_stats(Xf, yh.astype(np.float64))
+        # a second context (no communicator): the statistic / fit of the slice alone, exact kernel and tensor-core kernel
+        c2 = b2.Context(local_rank)
+        X2, y2 = c2.to_device(Xh, kind), c2.to_device(yh)
+        c2.set_kernel(b2.KERNEL_SIMT)
+        c2.gram_reset(D); c2.gram_accumulate(X2, y2)
+        S_dev = c2.gram_export()
+        c2.set_kernel(b2.KERNEL_TCGEN05)
+        c_tc, b_tc = c2.fit(X2, y2)
+        c2.close()
+        reg = LinearRegression().fit(Xf[:200_000], yh[:200_000].astype(np.float64))
+        ref = orc.fit_from_stats(S_np)
+        oracle_pin = {"rows": m,
+                      "exact_kernel_vs_numpy_oracle_statistic_rel": float(np.max(np.abs(S_dev - S_np)) / np.max(np.abs(S_np))),
+                      "tensor_core_fit_vs_numpy_oracle_coef_linf": float(np.max(np.abs(c_tc - ref["coef"]))),
+                      "tensor_core_fit_vs_numpy_oracle_intercept": float(abs(b_tc - ref["intercept"])),
+                      "oracle_vs_sklearn_fp64_coef_linf_200k": float(np.max(np.abs(
+                          orc.fit_from_stats(orc.gram_stats(Xf[:200_000], yh[:200_000].astype(np.float64)))["coef"] - reg.coef_))),
+                      "tolerance": 1e-4}
+        # (2) the reference's fit call, timed on the host cores
+        if world == 1:
+            sample_rows = 1_000_000
+            v, secs, _ = sklearn_fit_rows_per_s(sample_rows)
+            cpu = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "seconds": secs,
+                   "sample": f"{sample_rows} x {D} fp32 rows, one LinearRegression(fit_intercept=True).fit "
+                             f"(stage_1_train_model.py:105-106), all BLAS threads"}
+    if dist is not None:
+        dist.barrier()
+
+    # ---- the north-star point (N = 1): 100 M x 128 fp32 on ONE GPU; strong scaling of the same 100 M rows (N > 1) ------
+    north_star = None
+    strong = None
+    if extras and kind == "f32":
+        ns_rows = NORTH_STAR_ROWS // world
+        if world == 1 or ns_rows != rows:
+            X.free(); y.free()
+            Xn, yn = ctx.synth(ns_rows, D, seed=1234, row_offset=rank * ns_rows, kind="f32")
+            ns_ms, ns_kms, _l, ns_sol = time_fits(ctx, dist, Xn, yn, 5, 3, barrier)
+            chk = exact_check(ctx, b2, Xn, yn, D, ns_sol, dist, f"{ns_rows * world} x {D}")
+            rec = {"rows_total": ns_rows * world, "rows_per_gpu": ns_rows, "ms_per_fit": ns_ms / 5,
+                   "fit_rows_per_s": ns_rows * world / (ns_ms / 5) * 1e3, "gram_kernel_ms": ns_kms,
+                   "gram_kernel_frac_of_hbm_peak": ns_rows * 516 / ns_kms / 1e6 / peak,
+                   "whole_fit_frac_of_hbm_peak": ns_rows * 516 / (ns_ms / 5) / 1e6 / peak,
+                   "coef_linf_vs_exact": chk["coef_linf"], "intercept_abs_err_vs_exact": chk["intercept_abs_err"],
+                   "statistic_rel_err": chk["statistic_rel_err"], "rows_in_statistic": chk["rows_in_statistic"],
+                   "exact_kernel_seconds": chk["exact_kernel_seconds"],
+                   "bit_identical_across_ranks": chk.get("bit_identical_across_ranks"),
+                   "coef_head": [float(c) for c in ns_sol[0][:3]], "intercept": float(ns_sol[1])}
+            Xn.free(); yn.free()
+        else:
+            rec = {"rows_total": total_rows, "rows_per_gpu": rows, "ms_per_fit": ms / args.steps,
+                   "fit_rows_per_s": value, "note": "identical to the headline line (100 M rows over 8 GPUs)",
+                   "coef_linf_vs_exact": parity["coef_linf"]}
+        if world == 1:
+            rec["what"] = ("BASELINE.json north_star: >= 70 % of the HBM roofline on the Gram kernel at N = 100 M, "
+                           "D = 128 on 1 B200, coefficient error < 1e-4")
+            north_star = rec
+        else:
+            rec["what"] = (f"SURVEY 8(d) config 3: the SAME 100 M x 128 rows strong-scaled over {world} GPUs "
+                           f"(1 GPU: the `north_star` object of the N = 1 line)")
+            strong = rec
 
     if rank == 0:
         out = {
@@ -444,8 +599,9 @@ def main() -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ("bf16x2 (hi+lo)" if args.precision == "split" else "bf16x1") + " MMA operands, f32 accumulate, f64 fold+solve",
             "data": "synthetic (device Philox, reference DGP: X~U(0,100), y=1+0.5*sum(X)+10*eps)",
-            "config": workload_config(world, kind), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "variants": variants,
+            "config": workload_config(world, kind, rows), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "oracle_pin": oracle_pin, "exchange": exchange,
+            "score_shard": score_shard, "north_star": north_star, "strong_100M": strong, "config1_10Mx128": config1,
             "companion_score": companion,
             "host_wall_ms_per_step": 1e3 * t_host / args.steps,
             "coef_head": [float(c) for c in coef[:3]], "intercept": float(b0),

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "b2_ctx_set_kernel": (C.c_int, [_vp, C.c_int]),
     "b2_ctx_set_drain_rows": (C.c_int, [_vp, C.c_int]),
     "b2_ctx_set_precision": (C.c_int, [_vp, C.c_int]),
+    "b2_ctx_set_sm_limit": (C.c_int, [_vp, C.c_int]),
     "b2_dev_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "b2_dev_free": (C.c_int, [_vp, _vp]),
     "b2_host_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
@@ -266,6 +267,9 @@ class Context:
         """PRECISION_SPLIT (default, bf16 hi+lo operands) or PRECISION_BF16 (single bf16 operand, 'bf16-accum')."""
         _check(load().b2_ctx_set_precision(self._h, int(precision)), "b2_ctx_set_precision")
 
+    def set_sm_limit(self, n_sms: int) -> None:
+        _check(load().b2_ctx_set_sm_limit(self._h, int(n_sms)), "b2_ctx_set_sm_limit")
+
     def set_drain_rows(self, rows: int) -> None:
         _check(load().b2_ctx_set_drain_rows(self._h, int(rows)), "b2_ctx_set_drain_rows")
 
@@ -317,7 +321,7 @@ class Context:
     def fit(self, X, y, row_mask=None, mask_keep: int = 1, alpha: float = 0.0,
             fit_intercept: bool = True) -> Tuple[np.ndarray, float]:
         """The whole fit in one C call (b2_fit): reset + accumulate + all-reduce + solve.  Device-resident rows on the
-        tensor-core path run as two kernel launches.  Raises ``np.linalg.LinAlgError`` on a rank-deficient Gram."""
+        tensor-core path run as four launches (shift sample, Gram, finalize + peer scatter, gather + solve).  Raises ``np.linalg.LinAlgError`` on a rank-deficient Gram."""
         ptr, xdt, mk, n, d = _x_kind(X)
         yp = _vec_ptr(y, "f32", mk, n, "y")
         mp = _vec_ptr(row_mask, "u8", mk, n, "row_mask")

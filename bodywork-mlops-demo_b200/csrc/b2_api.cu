@@ -313,6 +313,12 @@ int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows) {
   return B2_OK;
 }
 
+int b2_ctx_set_sm_limit(b2_ctx* ctx, int n_sms) {
+  if (ctx == nullptr || n_sms < 0) { set_error("n_sms must be >= 0 (0 = all SMs)"); return B2_E_ARG; }
+  ctx->sm_limit = n_sms;
+  return B2_OK;
+}
+
 int b2_ctx_set_precision(b2_ctx* ctx, int precision) {
   if (ctx == nullptr || (precision != B2_PRECISION_SPLIT && precision != B2_PRECISION_BF16)) {
     set_error("precision must be B2_PRECISION_SPLIT or B2_PRECISION_BF16");
@@ -547,10 +553,11 @@ int b2_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept, double* singul
 }
 
 // ---- the whole fit in one call ----------------------------------------------------------------------------
-// reset + accumulate + all-reduce + solve.  Device-resident rows that take the tensor-core kernel run as TWO launches:
-// the Gram kernel (own shift sample, in-kernel reduce + fold of the per-CTA partials, S stored straight into the peers'
-// exchange slots) and the solve kernel (waits for the peers' slots, sums them, factors, writes the coefficients into
-// pinned host memory).  Everything else is the plain sequence of the four calls.
+// reset + accumulate + all-reduce + solve.  Device-resident rows that take the tensor-core kernel run as four launches
+// with no memset, no separate scatter / gather kernels and no D2H copy node: shift sample, Gram kernel, finalize kernel
+// (reduces and folds the per-CTA partials, overwrites S, stores it straight into the peers' exchange slots) and the
+// solve kernel (waits for the peers' slots, sums them, factors, writes the coefficients into pinned host memory).
+// Everything else is the plain sequence of the four calls.
 int b2_fit(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_rows, int d, int64_t ldx, int mem_kind,
            const uint8_t* row_mask, int mask_keep, double alpha, int fit_intercept, double* coef, double* intercept) {
   if (int r = use_device(ctx)) return r;
@@ -772,7 +779,7 @@ int b2_metrics(b2_ctx* ctx, const void* y_actual, const void* y_predicted, int d
   return B2_OK;
 }
 
-// counters of the context: [0] fits that took the fused two-launch path, [1] exchanges started, [2] kernels launched
+// counters of the context: [0] fits that took the fused path of b2_fit, [1] exchanges started, [2] kernels launched
 int b2_ctx_stats(b2_ctx* ctx, int64_t* out3) {
   if (ctx == nullptr || out3 == nullptr) { set_error("null argument"); return B2_E_ARG; }
   out3[0] = ctx->fused_fits;
@@ -899,6 +906,11 @@ int b2_comm_p2p_attach_local(b2_ctx* ctx, int n_ranks, int rank, b2_ctx* const* 
     }
     ctx->xchg_peer[r] = peers[r]->xchg;
   }
+  // contexts that share ONE device: a peer's kernel waiting for this rank's flags holds an SM, and the cooperative Gram
+  // launch needs all of its CTAs resident at once -- leave those SMs free (a test / single-GPU configuration)
+  int same_device = 0;
+  for (int r = 0; r < n_ranks; ++r) same_device += (r != rank && peers[r]->device == ctx->device) ? 1 : 0;
+  if (same_device > 0 && ctx->sm_limit == 0) ctx->sm_limit = ctx->sm_count - 9 * same_device;
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
   ctx->p2p_ready = true;

@@ -113,6 +113,7 @@ struct b2_ctx {
   // fused fit (b2_fit): in-kernel grid barrier / ticket words of the Gram kernel's reduce + fold tail
   unsigned int* tc_sync = nullptr;     // [0], [1] barrier arrivals, [2] ticket
   int fused_fits = 0;                  // fits that took the fused path (b2_ctx_stats)
+  int sm_limit = 0;                    // > 0: persistent kernels use at most this many SMs (b2_ctx_set_sm_limit)
 };
 
 namespace b2 {

@@ -168,7 +168,6 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
 // ------------------------------------------------------------------------------------------
 constexpr int kShiftBlocks = 64;                 // partial sums of the row sample, one per block
 constexpr int kShiftStride = kMaxD + 1;          // floats per partial: features, then y (slot kMaxD)
-constexpr int kFusedSamples = 256;               // rows of the in-kernel shift sample (fused fit); <= kThreads
 
 __host__ __device__ __forceinline__ int64_t shift_samples(int64_t n) { return n < 2048 ? n : 2048; }
 
@@ -228,15 +227,22 @@ __device__ __forceinline__ void tc_reduce_range(const double* part, const double
       }
       for (; c < c1; ++c) acc[0] += __ldcg(part + (size_t)c * kTcAccElems + idx);
       quarter[q * epb + e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    } else if (idx < e1 && idx < kRedElems && q == 0) {
+    } else if (idx < e1 && idx < kRedElems) {
+      // the three CUDA-core sums (sum y', sum y'^2, rows): same quarter scheme, loads 8 deep (a serial walk over the
+      // CTAs costs one L2 round trip each: 148 x ~140 ns was most of this phase)
       const int k = idx - kTcAccElems;
-      double s = 0.0;
-      for (int c = 0; c < n_ctas; ++c)
-        s += __ldcg(side + (size_t)c * kTcSideDoubles + k) + __ldcg(side + (size_t)c * kTcSideDoubles + 3 + k);
-      red[idx] = s;
+      double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      int c = c0;
+      for (; c + 8 <= c1; c += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          acc[u] += __ldcg(side + (size_t)(c + u) * kTcSideDoubles + k) + __ldcg(side + (size_t)(c + u) * kTcSideDoubles + 3 + k);
+      }
+      for (; c < c1; ++c) acc[0] += __ldcg(side + (size_t)c * kTcSideDoubles + k) + __ldcg(side + (size_t)c * kTcSideDoubles + 3 + k);
+      quarter[q * epb + e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     }
     __syncthreads();
-    if (q == 0 && idx < e1 && idx < kTcAccElems)
+    if (q == 0 && idx < e1 && idx < kRedElems)
       red[idx] = ((quarter[e] + quarter[epb + e]) + quarter[2 * epb + e]) + quarter[3 * epb + e];
     __syncthreads();
   }
@@ -319,21 +325,6 @@ __device__ __forceinline__ double tc_fold_value(const double* red, const CT* c, 
 }
 
 
-// what the fused tail needs (passed by value; fused == 0: the host launches tc_reduce_kernel / tc_fold_kernel)
-struct TcTail {
-  int fused;
-  int assign;                 // S = value instead of S += value
-  unsigned int* sync;         // [0], [1]: grid barriers, [2]: ticket
-  double* red;
-  double* S;
-  const void* X_raw;          // original rows for the in-kernel shift sample
-  const float* y_raw;
-  int64_t ldx_raw;
-  int n_ranks, rank;          // n_ranks > 1: scatter S to the peers' exchange slots and publish
-  unsigned int epoch;
-  PeerPtrs peers;
-};
-
 // ------------------------------------------------------------------------------------------
 // the Gram kernel
 // ------------------------------------------------------------------------------------------
@@ -348,8 +339,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep,
                int64_t n_rows, int d_arg, int pack, int d_orig, int64_t n_shift, const float* __restrict__ shift,
                int chunk_tiles,
-               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg,
-               const TcTail tail) {
+               double* __restrict__ part, double* __restrict__ side, uint32_t wait_ns, uint32_t dbg_arg) {
 #ifdef B2_DEV_KNOBS
   const uint32_t dbg = dbg_arg;      // ablation switches (tools/build_dev.sh): results are WRONG when non-zero
 #else
@@ -412,45 +402,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
   // packed rows (pack > 1): super-row feature i < pack * d_orig is original feature i % d_orig -> the shift repeats;
   // the columns from pack * d_orig to 127 are TMA out-of-bounds zero fill and keep shift 0 (they contribute nothing)
-  if (tail.fused) {
-    // fused fit: no separate shift kernel -- every CTA derives the same c from a strided sample of the original rows
-    // (kFusedSamples rows; any c near the column mean keeps the shifted Gram well conditioned, the fold is exact for
-    // every c).  The sample is 66 KB at D = 128: one DRAM read, L2 hits for the other 147 CTAs.
-    float* scratch = reinterpret_cast<float*>(smem + kOffRaw);          // [6 groups][128] + [24 warps]: raw stage 0 is idle
-    const int64_t samples = n_shift < kFusedSamples ? n_shift : kFusedSamples;
-    const int64_t stride = n_shift / samples;
-    const int col = threadIdx.x & 127, grp = threadIdx.x >> 7;          // 768 threads = 6 row groups x 128 columns
-    float acc = 0.f;
-    if (col < d_orig) {
-      const T* Xr = static_cast<const T*>(tail.X_raw);
-#pragma unroll 4
-      for (int64_t sidx = grp; sidx < samples; sidx += kThreads / 128)
-        acc += raw_ld_global<T>(Xr + sidx * stride * tail.ldx_raw + col);
-    }
-    scratch[grp * 128 + col] = acc;
-    float ya = (threadIdx.x < samples) ? __ldg(tail.y_raw + (int64_t)threadIdx.x * stride) : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ya += __shfl_xor_sync(0xffffffffu, ya, o);
-    if (lane == 0) scratch[kThreads + warp] = ya;
-    __syncthreads();
-    float cval = 0.f;
-    if (threadIdx.x < 128) {
-      for (int g = 0; g < kThreads / 128; ++g) cval += scratch[g * 128 + threadIdx.x];
-      cval = threadIdx.x < d_orig ? __bfloat162float(__float2bfloat16_rn(cval / (float)samples)) : 0.f;
-    } else if (threadIdx.x == 128) {
-      for (int w = 0; w < kThreads / 32; ++w) cval += scratch[kThreads + w];
-      cval = __bfloat162float(__float2bfloat16_rn(cval / (float)samples));
-    }
-    __syncthreads();
-    if (threadIdx.x <= 128) scratch[threadIdx.x] = cval;                // [0, 128): c_j, [128]: c_y
-    __syncthreads();
-    for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
-      shift_s[j] = (j == kMaxD) ? scratch[128] : (j < pack * d_orig ? scratch[j % d_orig] : 0.f);
-  } else {
-    for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
-      shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift)
-                                : (j < pack * d_orig ? shift_value(shift, j % d_orig, n_shift) : 0.f);
-  }
+  for (int j = threadIdx.x; j <= kMaxD; j += kThreads)
+    shift_s[j] = (j == kMaxD) ? shift_value(shift, kMaxD, n_shift)
+                              : (j < pack * d_orig ? shift_value(shift, j % d_orig, n_shift) : 0.f);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -717,48 +671,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
-  if (!tail.fused) return;
-
-  // ---- fused finalize (b2_fit): reduce the per-CTA partials, fold into S, scatter to the peers ---------------
-  // The grid is launched cooperatively (all CTAs co-resident), so a counter barrier is safe.  Every CTA's partial
-  // stores precede its arrival (the __syncthreads above orders the epilogue warps, the barrier fences).
-  double* quarter = reinterpret_cast<double*>(smem + kOffRaw);            // 4 * 192 doubles; the pipeline is drained
-  const int n_ctas = (int)gridDim.x;
-  grid_barrier(tail.sync + 0);
-  {
-    const int per = (((kRedElems + n_ctas - 1) / n_ctas) + 63) & ~63;
-    const int e0 = (int)blockIdx.x * per;
-    const int e1 = e0 + per < kRedElems ? e0 + per : kRedElems;
-    if (e0 < kRedElems) tc_reduce_range(part, side, n_ctas, tail.red, e0, e1, quarter);
-  }
-  grid_barrier(tail.sync + 1);
-  {
-    const int dp = d_orig + 2;
-    const int total = dp * dp;
-    const int per = (total + n_ctas - 1) / n_ctas;
-    const int i0 = (int)blockIdx.x * per;
-    const int i1 = i0 + per < total ? i0 + per : total;
-    const size_t slot = xchg_slot_offset(tail.epoch, tail.rank);
-    for (int idx = i0 + (int)threadIdx.x; idx < i1; idx += kThreads) {
-      const double val = tc_fold_value(tail.red, shift_s, d_orig, pack, idx);
-      const double sv = tail.assign ? val : tail.S[idx] + val;
-      tail.S[idx] = sv;
-      if (tail.n_ranks > 1) xchg_store_all(tail.peers, tail.n_ranks, slot, idx, sv);
-    }
-    if (tail.n_ranks > 1) __threadfence_system();
-  }
-  __syncthreads();
-  __shared__ bool last_cta;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last_cta = (atomicAdd(tail.sync + 2, 1u) == gridDim.x - 1);
-    if (last_cta) {                       // every CTA has passed both barriers: re-arm them for the next launch
-      tail.sync[0] = 0u; tail.sync[1] = 0u; tail.sync[2] = 0u;
-      __threadfence();
-    }
-  }
-  __syncthreads();
-  if (last_cta && tail.n_ranks > 1) xchg_publish(tail.peers, tail.n_ranks, tail.rank, tail.epoch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -767,29 +679,63 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 //   red[kTcAccElems + 0..2]            : sum y', sum y'^2, rows used
 // tc_fold_kernel undoes the shift in fp64 and adds the result into the raw statistic S ((d+2)^2, stride d+2).
 // ------------------------------------------------------------------------------------------
-constexpr int kFinalizeThreads = 256;
-constexpr int kRedShiftOff = kTcAccElems + 16;   // red[kRedShiftOff + j]: the shift c_j as fp64 (j = kMaxD: c_y)
 
-// finalize 1: reduce the per-CTA partials (one extra block materialises the shift vector for finalize 2)
-__global__ void __launch_bounds__(kFinalizeThreads)
-tc_reduce_kernel(const double* __restrict__ part, const double* __restrict__ side, int n_ctas,
-                 double* __restrict__ red, const float* __restrict__ shift, int64_t n_rows, int d) {
-  if (blockIdx.x == gridDim.x - 1) {
-    for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
-      red[kRedShiftOff + j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
-    return;
+// What tc_finalize_kernel does after the reduce + fold (passed by value).
+struct TcFinal {
+  int assign;                 // S = value instead of S += value (fresh statistic: no memset launch)
+  int n_ranks, rank;          // n_ranks > 1: store S into the exchange slot of every rank and publish the flags
+  unsigned int epoch;
+  PeerPtrs peers;
+};
+
+// ONE launch behind the Gram kernel: reduce the per-CTA partials (fixed order: deterministic), grid barrier, undo the
+// shift in fp64 and fold into S, store S into the peers' exchange slots (b2_fit with an attached peer exchange), and
+// -- through a last-block ticket -- publish the exchange flags and re-arm the barrier.  Cooperative launch: every CTA
+// is resident, so the counter barrier is safe.  This work deliberately does NOT live in the Gram kernel's tail: with
+// it there (even out of line) the hot role loops lost 5 % (same box: 0.807 ms without, 0.849 ms with, 10 M x 128
+// rows) -- more than the launch it saves.
+constexpr int kFinalizeThreads = 1024;                           // 4 threads per element of the partials
+constexpr int kFinalizeCtas = (kRedElems + kFinalizeThreads / 4 - 1) / (kFinalizeThreads / 4);   // 145: one pass
+
+__global__ void __launch_bounds__(kFinalizeThreads, 1)
+tc_finalize_kernel(const double* part, const double* side, int n_ctas, double* red, const float* __restrict__ shift,
+                   int64_t n_rows, int d, int pack, double* S, unsigned int* sync, const TcFinal fin) {
+  __shared__ double quarter[kFinalizeThreads];
+  __shared__ double c_s[kMaxD + 1];                              // the shift as fp64 (c_s[kMaxD]: c_y)
+  for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
+    c_s[j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
+  {
+    constexpr int epb = kFinalizeThreads / 4;                    // elements per pass of a CTA
+    const int per = (((kRedElems + (int)gridDim.x - 1) / (int)gridDim.x) + epb - 1) / epb * epb;
+    const int e0 = (int)blockIdx.x * per;
+    const int e1 = e0 + per < kRedElems ? e0 + per : kRedElems;
+    if (e0 < kRedElems) tc_reduce_range(part, side, n_ctas, red, e0, e1, quarter);
   }
-  __shared__ double quarter[4 * (kFinalizeThreads / 4)];
-  const int e0 = blockIdx.x * (kFinalizeThreads / 4);
-  const int e1 = e0 + kFinalizeThreads / 4 < kRedElems ? e0 + kFinalizeThreads / 4 : kRedElems;
-  tc_reduce_range(part, side, n_ctas, red, e0, e1, quarter);
-}
-
-// finalize 2: one thread per element of S
-__global__ void __launch_bounds__(kFinalizeThreads)
-tc_fold_kernel(const double* __restrict__ red, int d, int pack, double* __restrict__ S) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < (d + 2) * (d + 2)) S[idx] += tc_fold_value(red, red + kRedShiftOff, d, pack, idx);
+  grid_barrier(sync + 0);
+  {
+    const int dp = d + 2;
+    const int total = dp * dp;
+    const size_t slot = xchg_slot_offset(fin.epoch, fin.rank);
+    for (int idx = (int)(blockIdx.x * blockDim.x + threadIdx.x); idx < total; idx += (int)(gridDim.x * blockDim.x)) {
+      const double val = tc_fold_value(red, c_s, d, pack, idx);
+      const double sv = fin.assign ? val : S[idx] + val;
+      S[idx] = sv;
+      if (fin.n_ranks > 1) xchg_store_all(fin.peers, fin.n_ranks, slot, idx, sv);
+    }
+    if (fin.n_ranks > 1) __threadfence_system();
+  }
+  __syncthreads();
+  __shared__ bool last_cta;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_cta = (atomicAdd(sync + 2, 1u) == gridDim.x - 1);
+    if (last_cta) {                       // every CTA has passed the barrier: re-arm it for the next launch
+      sync[0] = 0u; sync[2] = 0u;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (last_cta && fin.n_ranks > 1) xchg_publish(fin.peers, fin.n_ranks, fin.rank, fin.epoch);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -958,7 +904,8 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   }
 
   const int64_t total_tiles = (n + kTcRows - 1) / kTcRows;
-  const int grid = (int)(total_tiles < ctx->sm_count ? total_tiles : ctx->sm_count);
+  const int sms = (ctx->sm_limit > 0 && ctx->sm_limit < ctx->sm_count) ? ctx->sm_limit : ctx->sm_count;
+  const int grid = (int)(total_tiles < sms ? total_tiles : sms);
   int chunk_tiles = ctx->drain_rows / kTcRows;
   if (chunk_tiles < 1) chunk_tiles = 1;
 
@@ -973,32 +920,18 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     ctx->tc_attr_set = true;
   }
 
-  const bool fused = fuse != nullptr;
-  if (!fused) {
+  // S: a fresh statistic is overwritten by the finalize kernel (no memset launch); otherwise it must be cleared first
+  const bool assign = fuse != nullptr && fuse->assign != 0;
+  if (!assign) {
     if (int r = ensure_s_cleared(ctx)) return r;
-    if (x_dtype == B2_F32)
-      tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
-                                                                    ldx_in, ctx->shift);
-    else
-      tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
-                                                                            n_in, d_in, ldx_in, ctx->shift);
-    B2_CUDA(cudaGetLastError());
   }
-  TcTail tail;
-  memset(&tail, 0, sizeof(tail));
-  tail.fused = fused ? 1 : 0;
-  tail.red = ctx->tc_red;
-  tail.S = ctx->S;
-  tail.sync = ctx->tc_sync;
-  tail.X_raw = X; tail.y_raw = y; tail.ldx_raw = ldx_in;
-  tail.n_ranks = 1;
-  if (fused) {
-    tail.assign = fuse->assign;
-    if (fuse->scatter) {
-      tail.n_ranks = ctx->n_ranks; tail.rank = ctx->rank; tail.epoch = fuse->epoch;
-      for (int r = 0; r < kMaxRanks; ++r) tail.peers.p[r] = ctx->xchg_peer[r];
-    }
-  }
+  if (x_dtype == B2_F32)
+    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
+                                                                  ldx_in, ctx->shift);
+  else
+    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
+                                                                          n_in, d_in, ldx_in, ctx->shift);
+  B2_CUDA(cudaGetLastError());
 
 #ifdef B2_DEV_KNOBS
   static const uint32_t wait_ns = []() {   // development knob: suspend-time hint of the pipeline waits
@@ -1018,21 +951,11 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 #endif
   const int pair = ctx->k_pairs % kKernelEventPairs;
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][0], ctx->stream));
-  // the fused variant needs every CTA co-resident (grid barriers): cooperative launch, 1 CTA per SM by construction
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = fused ? 1 : 0;
-  const int has_mask_arg = mask != nullptr ? 1 + m_map_2d : 0;
-  const float* shift_arg = ctx->shift;
-  double* part_arg = ctx->tc_part; double* side_arg = ctx->tc_side;
-  cudaError_t lerr = cudaSuccess;
-#define B2_LAUNCH_TC(T, DF, SP)                                                                                     \
-  lerr = cudaLaunchKernelEx(&cfg, gram_tc_kernel<T, DF, SP>, tmX, tmY, tmM, y_map_2d, has_mask_arg, keep, n, d, pack, \
-                            d_in, n_in, shift_arg, chunk_tiles, part_arg, side_arg, wait_ns, dbg, tail)
+#define B2_LAUNCH_TC(T, DF, SP)                                                                          \
+  gram_tc_kernel<T, DF, SP><<<grid, kThreads, kSmemBytes, ctx->stream>>>(                                \
+      tmX, tmY, tmM, y_map_2d, mask != nullptr ? 1 + m_map_2d : 0, keep, n, d, pack, d_in, n_in, ctx->shift, \
+      chunk_tiles,                                                                                        \
+      ctx->tc_part, ctx->tc_side, wait_ns, dbg)
 #define B2_LAUNCH_TC_D(T, SP) \
   do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)
   const bool split = ctx->precision == B2_PRECISION_SPLIT;
@@ -1043,26 +966,37 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   }
 #undef B2_LAUNCH_TC_D
 #undef B2_LAUNCH_TC
-  B2_CUDA(lerr);
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaEventRecord(ctx->ev_k[pair][1], ctx->stream));
   ctx->k_pairs += 1;
 
-  if (!fused) {
-    tc_reduce_kernel<<<(kRedElems + 63) / 64 + 1, kFinalizeThreads, 0, ctx->stream>>>(
-        ctx->tc_part, ctx->tc_side, grid, ctx->tc_red, ctx->shift, n_in, d_in);
-    B2_CUDA(cudaGetLastError());
-    const int dp = d_in + 2;
-    tc_fold_kernel<<<(dp * dp + kFinalizeThreads - 1) / kFinalizeThreads, kFinalizeThreads, 0, ctx->stream>>>(
-        ctx->tc_red, d_in, pack, ctx->S);
-    B2_CUDA(cudaGetLastError());
-    ctx->launches += 4;
-    ctx->k_launches += 4;
-  } else {
-    ctx->launches += 1;
-    ctx->k_launches += 1;
-    ctx->s_zero_pending = false;   // the fold assigned (or added to an already cleared) S
+  // finalize: reduce + fold (+ peer scatter) in one cooperative launch
+  TcFinal fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.assign = assign ? 1 : 0;
+  fin.n_ranks = 1;
+  if (fuse != nullptr && fuse->scatter) {
+    fin.n_ranks = ctx->n_ranks; fin.rank = ctx->rank; fin.epoch = fuse->epoch;
+    for (int r = 0; r < kMaxRanks; ++r) fin.peers.p[r] = ctx->xchg_peer[r];
   }
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kFinalizeCtas < sms ? kFinalizeCtas : sms);
+    cfg.blockDim = dim3(kFinalizeThreads); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const double* part_arg = ctx->tc_part; const double* side_arg = ctx->tc_side;
+    const float* shift_arg = ctx->shift;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, tc_finalize_kernel, part_arg, side_arg, grid, ctx->tc_red, shift_arg, n_in, d_in, pack,
+                               ctx->S, ctx->tc_sync, fin));
+  }
+  ctx->launches += 3;
+  ctx->k_launches += 3;
+  ctx->s_zero_pending = false;
+  const bool fused = fuse != nullptr;
   if (n_main < n_in && !fused) {   // the n % pack leftover rows (the fused caller accumulates them first)
     const char* Xt = static_cast<const char*>(X) + (size_t)n_main * ldx_in * es;
     return launch_gram_simt(ctx, Xt, x_dtype, y + n_main, n_in - n_main, d_in, ldx_in,

@@ -11,7 +11,7 @@
 //                        fetches (b2_solve / b2_gram_export return B2_E_COMM instead of a fit on a partial statistic).
 //
 // These two launches serve the stand-alone b2_gram_allreduce call.  The fused fit (b2_fit, gram_tc.cu + solve.cu)
-// issues the same stores from the Gram kernel's fold and the same wait + sum from the solve kernel's prologue.
+// issues the same stores from the finalize kernel's fold and the same wait + sum from the solve kernel's prologue.
 #include "b2_xchg.cuh"
 
 namespace b2 {
@@ -50,14 +50,16 @@ __global__ void p2p_gather_kernel(double* __restrict__ S, int n_elems, double* o
 
 }  // namespace
 
+constexpr int kP2pCtas = 8;   // 135 KB per rank: latency bound; few CTAs, so a waiting gather leaves the SMs to the peers
+
 int launch_p2p_allreduce(b2_ctx* ctx) {
   const int n_elems = (ctx->d + 2) * (ctx->d + 2);
   PeerPtrs peers;
   for (int r = 0; r < kMaxRanks; ++r) peers.p[r] = ctx->xchg_peer[r];
   const unsigned int epoch = ++ctx->xchg_epoch;
-  p2p_scatter_kernel<<<16, 256, 0, ctx->stream>>>(ctx->S, n_elems, peers, ctx->n_ranks, ctx->rank, epoch);
+  p2p_scatter_kernel<<<kP2pCtas, 256, 0, ctx->stream>>>(ctx->S, n_elems, peers, ctx->n_ranks, ctx->rank, epoch);
   B2_CUDA(cudaGetLastError());
-  p2p_gather_kernel<<<16, 256, 0, ctx->stream>>>(ctx->S, n_elems, ctx->xchg, ctx->n_ranks, epoch, ctx->xchg_timeout_ns);
+  p2p_gather_kernel<<<kP2pCtas, 256, 0, ctx->stream>>>(ctx->S, n_elems, ctx->xchg, ctx->n_ranks, epoch, ctx->xchg_timeout_ns);
   B2_CUDA(cudaGetLastError());
   ctx->launches += 2;
   ctx->xchg_pending = true;

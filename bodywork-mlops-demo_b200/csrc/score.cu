@@ -57,6 +57,30 @@ struct RowStats {
     syp = fma(y, p, syp);
     mxape = fmax(mxape, rel);
   }
+  // Branch-free flavour for rows whose |y| is in the float range (checked per warp by the caller): the row is dropped
+  // by zeroing its inputs (use == false), so several rows per lane interleave without control flow between them.
+  // y arrives as the fp32 value it was stored as: the range test and the reciprocal seed need no fp64 conversion.
+  __device__ __forceinline__ void add_fast(float yf, double p, bool use) {
+    const double y = (double)(use ? yf : 0.f);
+    const double ps = use ? p : 0.0;
+    float rcf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcf) : "f"(use ? fabsf(yf) : 1.f));
+    const double r = y - ps;
+    const double e = fabs(r);
+    double rc = (double)rcf;
+    rc = fma(rc, fma(-fabs(y), rc, 1.0), rc);     // one Newton step: 2^-23 -> 2^-46 (use == false: finite, e == 0)
+    const double term = e * rc;
+    ape += term;
+    sse = fma(r, r, sse);
+    sy += y;
+    syy = fma(y, y, syy);
+    mx = fmax(mx, e);
+    rows += use ? 1 : 0;
+    sp += ps;
+    spp = fma(ps, ps, spp);
+    syp = fma(y, ps, syp);
+    mxape = fmax(mxape, term);
+  }
   // same ten statistics with correctly rounded divisions (b2_metrics: parity with the float64 reference to rounding)
   __device__ __forceinline__ void add_exact(double y, double p) {
     const double r = y - p, e = fabs(r), ay = fabs(y);
@@ -552,10 +576,17 @@ score_narrow_kernel(const T* __restrict__ X, int n_tiles, int d, const double* _
       mbar_wait(bar_full + 8 * s, phase);
       const uint32_t xs = sbase + s * G::kXStage, ys = sbase + G::kOffY + s * G::kYStage, ms = sbase + G::kOffM + s * G::kMStage;
       const int64_t row0 = (int64_t)tile * G::kRows;
+      // all rows of this lane first (loads, dot products, prediction store), then the statistics of all of them without
+      // control flow in between: the fp64 / conversion chains of the RPT rows interleave (the kernel was issue- and
+      // dependency-bound at D = 1: profiles/r02_score_narrow_*_summary.txt)
+      float yv[G::RPT];
+      double pr[G::RPT];
+      bool use[G::RPT];
+      bool fast = true;
 #pragma unroll
       for (int rr = 0; rr < G::RPT; ++rr) {
         const int r = rr * kSnConsumers + threadIdx.x;          // consecutive lanes, consecutive rows
-        const bool use = !has_mask || ld_shared_u8(ms + (uint32_t)r) == (uint32_t)keep;
+        use[rr] = !has_mask || ld_shared_u8(ms + (uint32_t)r) == (uint32_t)keep;
         float x[DP];
         if constexpr (EXACT) ld_vals_vec<T, DP>(xs + (uint32_t)r * row_bytes, x);
         else ld_vals_any<T, DP>(xs + (uint32_t)r * row_bytes, 0, d, x);
@@ -565,9 +596,21 @@ score_narrow_kernel(const T* __restrict__ X, int n_tiles, int d, const double* _
           a0 = fma((double)x[k], cf[k], a0);
           if (k + 1 < DP) a1 = fma((double)x[k + 1], cf[k + 1], a1);
         }
-        const double pr = a0 + a1;
-        if (yhat != nullptr) yhat[row0 + r] = use ? (float)pr : 0.f;
-        if (has_y && use) st.add((double)ld_shared_f32(ys + 4u * (uint32_t)r), pr);
+        pr[rr] = DP > 1 ? a0 + a1 : a0;
+        if (yhat != nullptr) yhat[row0 + r] = use[rr] ? (float)pr[rr] : 0.f;
+        yv[rr] = has_y ? ld_shared_f32(ys + 4u * (uint32_t)r) : 1.f;
+        const float ayf = fabsf(yv[rr]);
+        fast = fast && (!use[rr] || (ayf > 1e-30f && ayf < 1e30f));
+      }
+      if (has_y) {
+        if (__all_sync(0xffffffffu, fast)) {
+#pragma unroll
+          for (int rr = 0; rr < G::RPT; ++rr) st.add_fast(yv[rr], pr[rr], use[rr]);
+        } else {                                                 // a zero / huge label somewhere in the warp: exact path
+#pragma unroll
+          for (int rr = 0; rr < G::RPT; ++rr)
+            if (use[rr]) st.add((double)yv[rr], pr[rr]);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);

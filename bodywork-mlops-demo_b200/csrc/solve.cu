@@ -25,46 +25,60 @@ constexpr int kOutRank = kMaxD + 2;
 constexpr int kOutSingular = kMaxD + 3;
 constexpr int kOutRows = kOutSingular + kMaxD;   // eigvals kernel only
 
-// Builds A (pitch d+1) and r in shared memory from the raw statistic; returns means.
-__device__ void build_normal_equations(const double* S_in, int d, double alpha, int fit_intercept,
+// Builds A (pitch d+1) and r in shared memory from the raw statistic; returns means.  S is read through L2 (__ldcg: the
+// fused solve has just written it from this CTA) with the loads of a whole batch issued before the first use -- the
+// phase is two L2 round trips, not one per element.
+__device__ void build_normal_equations(const double* S, int d, double alpha, int fit_intercept,
                                        double* A, double* r, double* mean, double* ybar_out) {
-  const volatile double* S = S_in;   // the fused solve has just written S itself: plain loads, not the read-only path
   const int dp = d + 2, pitch = d + 1;
-  const double n = S[d * dp + d];
+  const double n = __ldcg(S + d * dp + d);
   const double inv_n = n > 0.0 ? 1.0 / n : 0.0;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) mean[j] = fit_intercept ? S[j * dp + d] * inv_n : 0.0;
+  double sxy = 0.0;
+  if ((int)threadIdx.x < d) {
+    const double sx = __ldcg(S + threadIdx.x * dp + d);
+    sxy = __ldcg(S + threadIdx.x * dp + d + 1);
+    mean[threadIdx.x] = fit_intercept ? sx * inv_n : 0.0;
+  }
+  const double ybar = fit_intercept ? __ldcg(S + d * dp + d + 1) * inv_n : 0.0;
   __syncthreads();
-  const double ybar = fit_intercept ? S[d * dp + d + 1] * inv_n : 0.0;
-  // one warp per row, coalesced; S is symmetric by construction (tc_fold / the SIMT reduce write both halves)
-  for (int i = threadIdx.x >> 5; i < d; i += blockDim.x >> 5) {
-    const double mi = mean[i];
-    for (int j = threadIdx.x & 31; j < d; j += 32) {
-      double v = S[i * dp + j] - n * mi * mean[j];
-      if (i == j) v += alpha;
-      A[i * pitch + j] = v;
+  if ((int)threadIdx.x < d) r[threadIdx.x] = sxy - n * mean[threadIdx.x] * ybar;
+  // S is symmetric by construction (tc_fold / the SIMT reduce write both halves).  One warp per row, lane = column
+  // (+32 u): no index division; two rows = 8 loads are issued before the first use.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i0 = warp; i0 < d; i0 += 2 * nwarps) {
+    const int i1 = i0 + nwarps;
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      v[u] = j < d ? __ldcg(S + i0 * dp + j) : 0.0;
+      v[4 + u] = (j < d && i1 < d) ? __ldcg(S + i1 * dp + j) : 0.0;
+    }
+    const double m0 = mean[i0], m1 = i1 < d ? mean[i1] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      if (j < d) {
+        const double mj = mean[j];
+        A[i0 * pitch + j] = v[u] - n * m0 * mj + (i0 == j ? alpha : 0.0);
+        if (i1 < d) A[i1 * pitch + j] = v[4 + u] - n * m1 * mj + (i1 == j ? alpha : 0.0);
+      }
     }
   }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) r[i] = S[i * dp + d + 1] - n * mean[i] * ybar;
   if (threadIdx.x == 0) *ybar_out = ybar;
   __syncthreads();
 }
 
-// 1/x for normal positive x without the library's slow-path division (a call inside the unrolled pivot loop forces the
-// register-resident block onto the stack, and a correctly rounded fp64 division is ~25 dependent instructions):
-// scale x by a power of two into [1, 2), fp32 MUFU seed y0 (relative error e ~ 2^-22), one cubic step
-// y = y0 (1 + e + e^2) (error e^3 ~ 2^-66, i.e. below the rounding of the last FMA), undo the scaling.
-// 6 dependent instructions after the conversion; the pivot recurrence of the factorisation is paced by this chain.
+// 1/x for positive x without the library division (measured on the B200, tools/ubench_fp64.cu: a dependent `1.0 / x` is
+// ~59 cycles, an fp64 FMA 8; a reciprocal seeded through fp32 conversions is slower still, ~100): the fp64 MUFU seed
+// (rcp.approx.ftz.f64, ~2^-20 relative) and one cubic step y = y0 (1 + e + e^2), e = 1 - x y0 -- error e^3, below the
+// rounding of the last FMA.  MUFU + 3 dependent FMAs; the pivot recurrence of the factorisation is paced by this chain.
 __device__ __forceinline__ double rcp_pos(double x) {
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const int e = ((hi >> 20) & 0x7ff) - 1023;
-  const double xs = __hiloint2double(hi - (e << 20), lo);               // x * 2^-e in [1, 2)
-  float y0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"((float)xs));
-  double y = (double)y0;
-  const double er = fma(-xs, y, 1.0);
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double er = fma(-x, y, 1.0);
   const double t = fma(er, er, er);
-  y = fma(y, t, y);
-  return __hiloint2double(__double2hiint(y) - (e << 20), __double2loint(y));   // y * 2^-e
+  return fma(y, t, y);
 }
 
 // Peer exchange consumed by the solve (fused fit, b2_fit): wait for the exchange, sum the slots into S.
@@ -79,11 +93,14 @@ struct SolveXchg {
 // lower triangular.  Carrying r as one extra row through the panel / update steps leaves w = D^-1 M^-1 r in that row, so
 // there is no forward substitution; the back substitution M^T b = w needs no division.  fp64 arithmetic here is
 // latency bound (the whole solve is 0.7 MFLOP), so every phase is written to keep the dependent chains short:
-//   (1) diagonal block: one warp, rows in registers, pivots by shuffle; the products u_ik u_ck are formed before the
-//       reciprocal of the pivot arrives, so the recurrence pivot -> next pivot is shuffle + rcp_pos (6) + one FMA;
-//   (2) panel: one thread per row, 2 dependent operations per column;
-//   (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m] (U = M D, the unscaled entries): 2 x 4 register tiles;
+//   (1) diagonal block: one warp, 16 rows x 2 column halves in registers, pivots by shuffle; the products u_ik u_ck are
+//       formed before the reciprocal of the pivot arrives, so the recurrence pivot -> next pivot is shuffle + rcp_pos +
+//       one FMA, and a lane issues at most 8 column updates per pivot (the phase is issue bound on its one warp);
+//   (2) panel: 4 lanes per row (the owner of column m broadcasts it inside the quad): shuffle + multiply + FMA per column;
+//   (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m] (U = M D, the unscaled entries) as 8 x 8 tiles on the fp64
+//       tensor-core path (DMMA m8n8k4), 4 per tile, tiles of the lower triangle dealt round-robin to the 16 warps;
 //   (4) back substitution per block in registers: shuffle + FMA per unknown.
+// Measured per phase at D = 128 (clock64, B200): profiles/r02_solve_phases.txt.
 // A is (d+1) x (d+1) with row pitch d+1 (fp64, shared memory); row d = r^T.  U: (d+1) x 16 panel scratch.
 constexpr int kNB = 16;
 constexpr int kCholThreads = 512;
@@ -116,7 +133,19 @@ solve_cholesky_kernel(double* S, int d, double alpha, int fit_intercept, double*
       return;
     }
     const int dp = d + 2;
-    for (int idx = tid; idx < dp * dp; idx += blockDim.x) S[idx] = xchg_sum(xc.own, xc.n_ranks, xc.epoch, idx);
+    for (int base = 0; base < dp * dp; base += 4 * blockDim.x) {      // 4 elements x n_ranks loads in flight per thread
+      double sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * blockDim.x + tid;
+        sv[u] = idx < dp * dp ? xchg_sum(xc.own, xc.n_ranks, xc.epoch, idx) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * blockDim.x + tid;
+        if (idx < dp * dp) S[idx] = sv[u];
+      }
+    }
     __threadfence();
     __syncthreads();
   }
@@ -136,101 +165,145 @@ solve_cholesky_kernel(double* S, int d, double alpha, int fit_intercept, double*
   for (int kb = 0; kb < d; kb += kNB) {
     const int nb = (d - kb) < kNB ? (d - kb) : kNB;
     tc0 = clock64();
-    // ---- (1) diagonal block: rows kb .. kb+nb-1 in the registers of lanes 0 .. nb-1 -------------------------------
+    // ---- (1) diagonal block: one warp, lane = (row, column parity): 16 rows x 2 halves, 8 columns per lane ----------
     if (warp == 0) {
-      double a[kNB], mm[kNB];
-      const int lrow = lane & (kNB - 1);
-      const int row = kb + (lrow < nb ? lrow : 0);
-      const bool act = lane < nb;
+      const int lrow = lane & (kNB - 1), h = lane >> 4;
+      const bool act = lrow < nb;
+      const int row = kb + (act ? lrow : 0);
+      double a[kNB / 2];                                  // a[cc] = A[row][kb + 2 cc + h]; only columns <= row are meaningful
 #pragma unroll
-      for (int c = 0; c < kNB; ++c) { a[c] = (act && c < nb) ? A[row * pitch + kb + c] : 0.0; mm[c] = 0.0; }
+      for (int cc = 0; cc < kNB / 2; ++cc) {
+        const int c = 2 * cc + h;
+        a[cc] = (act && c < nb) ? A[row * pitch + kb + c] : 0.0;
+      }
       double my_rc = 1.0;
       int first_bad = 0;
 #pragma unroll
       for (int k = 0; k < kNB; ++k) {
-        if (k < nb) {
-          const double piv = __shfl_sync(0xffffffffu, a[k], k);
+        if (k < nb) {                                     // warp-uniform
+          const int hk = k & 1, kk = k >> 1;              // column k lives in a[kk] of the lanes of half hk
+          const double colk = a[kk];
+          const double piv = __shfl_sync(0xffffffffu, colk, k | (hk << 4));
           const bool bad = !(piv > tiny);
           const double rc = bad ? 1.0 : rcp_pos(piv);
-          const double u = a[k];                        // lane > k: unscaled entry u_ik = m_ik * D_k
-          mm[k] = u * rc;                               // m_ik
-          my_rc = (lane == k) ? rc : my_rc;
+          const double u = __shfl_sync(0xffffffffu, colk, lrow | (hk << 4));   // u_ik = m_ik D_k of this lane's row
+          my_rc = (lrow == k) ? rc : my_rc;
           first_bad = (bad && first_bad == 0) ? (kb + k + 1) : first_bad;
 #pragma unroll
-          for (int c = k + 1; c < kNB; ++c) {
-            const double uc = __shfl_sync(0xffffffffu, u, c);   // u_ck
-            a[c] = fma(-(u * uc), rc, a[c]);                    // a_ic -= u_ik u_ck / D_k   (only c <= lane is meaningful)
+          for (int cc = 0; cc < kNB / 2; ++cc) {
+            if (2 * cc + 1 > k) {                         // compile time: some column of this slot is right of the pivot
+              const int c = 2 * cc + h;
+              const double uc = __shfl_sync(0xffffffffu, colk, c | (hk << 4));   // u_ck
+              if (c > k) a[cc] = fma(-(u * uc), rc, a[cc]);                      // a_ic -= u_ik u_ck / D_k
+            }
+          }
+          if (h == hk && act && lrow > k) {               // column k of the rows below the pivot: multiplier and raw entry
+            A[row * pitch + kb + k] = u * rc;
+            U[row * kUPitch + k] = u;
           }
         }
       }
-      __syncwarp();
-      if (act) {
-#pragma unroll
-        for (int c = 0; c < kNB; ++c) {
-          if (c < lane) { A[row * pitch + kb + c] = mm[c]; U[row * kUPitch + c] = a[c]; }
-        }
-        invd[kb + lane] = my_rc;
-      }
+      if (act && h == 0) invd[kb + lrow] = my_rc;
       if (lane == 0 && first_bad != 0 && misc[2] == 0.0) misc[2] = (double)first_bad;
     }
     __syncthreads();
     tm[1] += clock64() - tc0; tc0 = clock64();
     if (misc[2] != 0.0) break;
-    // ---- (2) panel: rows below the block (incl. the r row) ----------------------------------------------------------
-    const int below = rows - kb - nb;
-    for (int t = tid; t < below; t += blockDim.x) {
-      const int i = kb + nb + t;
-      double sv[kNB];
+    // ---- (2) panel: rows below the block (incl. the r row), 4 lanes per row (lane q owns columns c = q mod 4) ---------
+    {
+      const int prow = tid >> 2, q = tid & 3;
+      const int below = rows - kb - nb;                   // <= 113 <= blockDim / 4
+      const bool live = prow < below;
+      const int i = kb + nb + (live ? prow : 0);
+      double sv[4];
 #pragma unroll
-      for (int c = 0; c < kNB; ++c) sv[c] = c < nb ? A[i * pitch + kb + c] : 0.0;
+      for (int j = 0; j < 4; ++j) {
+        const int c = 4 * j + q;
+        sv[j] = (live && c < nb) ? A[i * pitch + kb + c] : 0.0;
+      }
+      const int qbase = lane & ~3;
+      double rinv[kNB];                                   // 1 / D of the block: loaded once, off the chain
+#pragma unroll
+      for (int m = 0; m < kNB; ++m) rinv[m] = m < nb ? invd[kb + m] : 0.0;
+      double out_m[4], out_u[4];                          // this lane's results (columns m = 4 j + q), stored after the
+#pragma unroll                                            // loop so that the loads of U below are free to move up
+      for (int j = 0; j < 4; ++j) { out_m[j] = 0.0; out_u[j] = 0.0; }
 #pragma unroll
       for (int m = 0; m < kNB; ++m) {
-        if (m < nb) {
-          const double um = sv[m];
-          const double xm = um * invd[kb + m];
-          A[i * pitch + kb + m] = xm;
-          U[i * kUPitch + m] = um;
+        if (m < nb) {                                     // block-uniform
+          const double um = __shfl_sync(0xffffffffu, sv[m >> 2], qbase | (m & 3));
+          const double xm = um * rinv[m];
+          if (q == (m & 3)) { out_m[m >> 2] = xm; out_u[m >> 2] = um; }
 #pragma unroll
-          for (int c = m + 1; c < kNB; ++c) if (c < nb) sv[c] = fma(-xm, U[(kb + c) * kUPitch + m], sv[c]);
+          for (int j = 0; j < 4; ++j) {
+            if (4 * j + 3 > m) {                          // compile time
+              const int c = 4 * j + q;
+              if (c > m && c < nb) sv[j] = fma(-xm, U[(kb + c) * kUPitch + m], sv[j]);
+            }
+          }
+        }
+      }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = 4 * j + q;
+          if (m < nb) { A[i * pitch + kb + m] = out_m[j]; U[i * kUPitch + m] = out_u[j]; }
         }
       }
     }
     __syncthreads();
     tm[2] += clock64() - tc0; tc0 = clock64();
-    // ---- (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m], i >= j >= kb+nb (i up to the r row) ---------------
-    // each thread owns a 2-row x 4-column register tile: 8 independent fp64 chains, one shared-memory load per
-    // two FMAs (the panel rows M[i][.] stay in registers)
-    const int ty = tid >> 4, tx = tid & 15;           // 32 x 16 thread grid
-    const int base = kb + nb;
-    for (int i0 = base + ty; i0 < rows; i0 += 64) {
-      const int i1 = i0 + 32;
-      const bool has1 = i1 < rows;
-      double p0[kNB], p1[kNB];
+    // ---- (3) trailing update A[i][j] -= sum_m M[i][m] U[j][m] on the fp64 tensor-core path -----------------------------
+    // 8 x 8 tiles of the lower triangle (i up to the r row), one DMMA m8n8k4 per 4 columns of the panel; a warp takes
+    // every 16th tile.  Fragments (PTX mma.m8n8k4.f64): A row = lane / 4, col = lane % 4; B row(k) = lane % 4,
+    // col(n) = lane / 4; C row = lane / 4, cols = 2 (lane % 4) + {0, 1}.
+    {
+      const int base = kb + nb;
+      const int nti = (rows - base + 7) >> 3, ntj = (d - base + 7) >> 3;
+      const int tri = ntj * (ntj + 1) / 2;
+      const int total = tri + (nti > ntj ? ntj : 0);      // the r row may start one more tile row
+      const int g = lane >> 2, t4 = lane & 3;
+      constexpr int kWarps = kCholThreads / 32, kInFlight = 4;
+      for (int t0 = warp; t0 < total; t0 += kWarps * kInFlight) {     // kInFlight independent tiles per pass: the loads and
+        int ia[kInFlight], jb[kInFlight];                             // the 4-deep DMMA chains of the tiles overlap
+        double c0[kInFlight], c1[kInFlight], av[kInFlight][kNB / 4], bv[kInFlight][kNB / 4];
 #pragma unroll
-      for (int m = 0; m < kNB; ++m) {
-        p0[m] = m < nb ? A[i0 * pitch + kb + m] : 0.0;
-        p1[m] = (m < nb && has1) ? A[i1 * pitch + kb + m] : 0.0;
-      }
-      const int jmax0 = i0 < d ? i0 : d - 1;
-      const int jmax1 = has1 ? (i1 < d ? i1 : d - 1) : -1;
-      const int jmax = jmax1 > jmax0 ? jmax1 : jmax0;
-      for (int j0 = base + tx; j0 <= jmax; j0 += 64) {
-        double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int m = 0; m < kNB; ++m) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 16 * u;
-            const double pj = (m < nb && j <= jmax) ? U[j * kUPitch + m] : 0.0;
-            a0[u] = fma(p0[m], pj, a0[u]);
-            a1[u] = fma(p1[m], pj, a1[u]);
+        for (int f = 0; f < kInFlight; ++f) {
+          const int t = t0 + f * kWarps;
+          int ti = 0, tj = 0;
+          if (t < tri) {
+            ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            tj = t - ti * (ti + 1) / 2;
+          } else if (t < total) {
+            ti = ntj; tj = t - tri;
           }
+          const bool live = t < total;
+          ia[f] = live ? base + 8 * ti + g : rows;                    // out of range: loads give 0, nothing is stored
+          jb[f] = live ? base + 8 * tj + g : d;
+#pragma unroll
+          for (int sgm = 0; sgm < kNB / 4; ++sgm) {
+            const int m = 4 * sgm + t4;
+            av[f][sgm] = (ia[f] < rows && m < nb) ? -A[ia[f] * pitch + kb + m] : 0.0;
+            bv[f][sgm] = (jb[f] < d && m < nb) ? U[jb[f] * kUPitch + m] : 0.0;
+          }
+          c0[f] = 0.0; c1[f] = 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 16 * u;
-          if (j <= jmax0) A[i0 * pitch + j] -= a0[u];
-          if (j <= jmax1) A[i1 * pitch + j] -= a1[u];
+        for (int sgm = 0; sgm < kNB / 4; ++sgm) {
+#pragma unroll
+          for (int f = 0; f < kInFlight; ++f)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c0[f]), "+d"(c1[f]) : "d"(av[f][sgm]), "d"(bv[f][sgm]));
+        }
+#pragma unroll
+        for (int f = 0; f < kInFlight; ++f) {
+          const int jc = jb[f] - g + 2 * t4;
+          if (ia[f] < rows) {
+            if (jc < d) A[ia[f] * pitch + jc] += c0[f];
+            if (jc + 1 < d) A[ia[f] * pitch + jc + 1] += c1[f];
+          }
         }
       }
     }
@@ -419,53 +492,85 @@ solve_spectral_kernel(const double* __restrict__ S, int d, double cond, int fit_
 //       characteristic-polynomial recurrence (one dependent FMA per row, power-of-two rescaling every 8 rows) at the 4
 //       interior points of its bracket, so every round shrinks every bracket 5x with no block-level synchronisation.
 constexpr int kEigThreads = 512;
+constexpr int kEigCols = kMaxD / 4;      // columns per thread: thread (row, q) keeps A[row][4 jj + q] in registers
 
-__device__ __forceinline__ int sturm_count(const double* __restrict__ dd, const double* __restrict__ ee2, int d, double x) {
-  // number of eigenvalues of T below x = sign changes of p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e_{i-2}^2 p_{i-2}
+// number of eigenvalues of T below x = sign changes of p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e_{i-2}^2 p_{i-2}.
+// dp8 = d rounded up to 8; rows d .. dp8-1 are decoupled 1 x 1 blocks far above the spectrum (no sign change).  Unrolled
+// by 8: the loads of a group do not depend on the recurrence, the chain is one FMA (+ the zero test) per row.
+__device__ __forceinline__ int sturm_count(const double* __restrict__ dd, const double* __restrict__ ee2, int dp8, double x) {
   double pm = 1.0, p = dd[0] - x;
+  if (p == 0.0) p = -1e-300;
   int count = p < 0.0 ? 1 : 0;
-  if (p == 0.0) { p = -1e-300; count = 1; }
-  for (int i = 1; i < d; ++i) {
-    double pn = fma(dd[i] - x, p, -(ee2[i - 1] * pm));
-    if (pn == 0.0) pn = (p < 0.0) ? 1e-300 : -1e-300;               // a zero counts as a sign change
-    count += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
-    pm = p; p = pn;
-    if ((i & 7) == 7) {                                              // keep the pair in range: scale both by 2^-exponent(p)
-      const int eb = (__double2hiint(p) >> 20) & 0x7ff;
-      int sh = 1023 - eb;
-      sh = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
-      const double sc = __hiloint2double((1023 + sh) << 20, 0);
-      p *= sc; pm *= sc;
+  double eprev = 0.0;                                                                   // e_{i-1}^2 of the row before the group
+  for (int i0 = 0; i0 < dp8; i0 += 8) {
+    double dv[8], ev[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { dv[u] = dd[i0 + u] - x; ev[u] = ee2[i0 + u]; }     // ee2[i] couples rows i and i + 1
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u > 0) {                                                                 // row 0 is p_1 above
+        double pn = fma(dv[u], p, -((u == 0 ? eprev : ev[u - 1]) * pm));
+        if (pn == 0.0) pn = (p < 0.0) ? 1e-300 : -1e-300;                               // a zero counts as a sign change
+        count += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+        pm = p; p = pn;
+      }
     }
+    eprev = ev[7];
+    const int eb = (__double2hiint(p) >> 20) & 0x7ff;                                   // keep the pair in range: 2^-exponent(p)
+    int sh = 1023 - eb;
+    sh = sh > 1000 ? 1000 : (sh < -1000 ? -1000 : sh);
+    const double sc = __hiloint2double((1023 + sh) << 20, 0);
+    p *= sc; pm *= sc;
   }
   return count;
 }
 
 __global__ void __launch_bounds__(kEigThreads, 1)
 solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, double* __restrict__ out) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int pitch = d + 1;
-  double* A = sm;                         // symmetric, full storage (both triangles kept current)
+  double* A = sm;                         // symmetric, full storage; lives in registers during the tridiagonalisation
   double* r = A + d * pitch;              // (unused here; build_normal_equations fills it)
   double* mean = A + (d + 1) * pitch;
   double* misc = mean + 2 * d;
-  double* v = misc + 8;                   // Householder vector (v[k+1] = 1)
-  double* pv = v + d;                     // tau * A v
-  double* dd = pv + d;                    // diagonal of T
-  double* ee2 = dd + d;                   // squared off-diagonal of T
-  double* lam = ee2 + d;                  // eigenvalues, ascending
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // [2][kMaxD]: (v_j, w_j) of the current reflection, by step parity; 16-byte aligned (the offset in doubles made even)
+  double2* vw = reinterpret_cast<double2*>(sm + ((((size_t)(misc + 8 - sm)) + 1) & ~(size_t)1));
+  double* pv = reinterpret_cast<double*>(vw + 2 * kMaxD);   // [kMaxD] tau * A v
+  double* dd = pv + kMaxD;                // [kMaxD + 8] diagonal of T (padded for the unrolled Sturm recurrence)
+  double* ee2 = dd + kMaxD + 8;           // [kMaxD + 8] squared off-diagonal of T
+  double* lam = ee2 + kMaxD + 8;          // [kMaxD] eigenvalues, ascending
+  const int tid = threadIdx.x, lane = tid & 31;
   build_normal_equations(S, d, 0.0, fit_intercept, A, r, mean, &misc[0]);
 
-  for (int k = 0; k + 2 < d; ++k) {
-    const int m = d - k - 1;              // length of the column below the diagonal: rows k+1 .. d-1
-    // (a1) reflection: x = A[k+1.., k] (read as the row k, A is symmetric); beta = -sign(x0) |x|, tau = (beta - x0) / beta
-    if (warp == 0) {
-      double s2 = 0.0;
-      for (int i = lane + 1; i < m; i += 32) { const double x = A[k * pitch + k + 1 + i]; s2 = fma(x, x, s2); }
+  // ---- (a) Householder tridiagonalisation, the matrix in registers: thread (row, q) owns columns j = 4 jj + q ----------
+  const int row = tid >> 2, q = tid & 3;
+  double a[kEigCols];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-      const double x0 = A[k * pitch + k + 1];
+  for (int jj = 0; jj < kEigCols; ++jj) {
+    const int j = 4 * jj + q;
+    a[jj] = (row < d && j < d) ? A[row * pitch + j] : 0.0;
+  }
+  for (int j = tid; j < 2 * kMaxD; j += blockDim.x) vw[j] = make_double2(0.0, 0.0);
+  for (int j = tid; j < kMaxD; j += blockDim.x) pv[j] = 0.0;
+  __syncthreads();
+  for (int k = 0; k + 2 < d; ++k) {
+    double2* vwk = vw + (k & 1) * kMaxD;
+    // (a1) the reflector of column k, by the 4 threads that own row k (= column k, the matrix is symmetric):
+    //      x = A[k][k+1 ..]; beta = -sign(x0) |x|, tau = (beta - x0) / beta, v = x / (x0 - beta), v[k+1] = 1
+    if (row == k) {
+      const unsigned int qmask = 0xFu << (lane & ~3);
+      double s2 = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < kEigCols; ++jj) {
+        const int j = 4 * jj + q;
+        if (j > k + 1) s2 = fma(a[jj], a[jj], s2);
+        if (j == k + 1) misc[6] = a[jj];
+        if (j == k) misc[7] = a[jj];
+      }
+      s2 += __shfl_xor_sync(qmask, s2, 1);
+      s2 += __shfl_xor_sync(qmask, s2, 2);
+      __syncwarp(qmask);
+      const double x0 = misc[6];
       double tau = 0.0, beta = x0, scale = 0.0;
       if (s2 > 0.0) {
         const double nrm = sqrt(fma(x0, x0, s2));
@@ -473,45 +578,59 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
         tau = (beta - x0) / beta;
         scale = 1.0 / (x0 - beta);
       }
-      for (int i = lane; i < m; i += 32) v[k + 1 + i] = (i == 0) ? 1.0 : A[k * pitch + k + 1 + i] * scale;
-      if (lane == 0) { misc[1] = tau; dd[k] = A[k * pitch + k]; ee2[k] = beta * beta; }
+#pragma unroll
+      for (int jj = 0; jj < kEigCols; ++jj) {
+        const int j = 4 * jj + q;
+        if (j < d) vwk[j].x = (j > k + 1) ? a[jj] * scale : (j == k + 1 ? 1.0 : 0.0);
+      }
+      if (q == 0) { misc[1] = tau; dd[k] = misc[7]; ee2[k] = beta * beta; }
     }
     __syncthreads();
     const double tau = misc[1];
     if (tau != 0.0) {                     // block-uniform
-      // (a2) p = tau * A22 v: 4 threads per row
-      {
-        const int row = tid >> 2, q = tid & 3;
-        double acc = 0.0;
-        if (row < m) {
-          const double* ar = A + (k + 1 + row) * pitch + k + 1;
-          for (int j = q; j < m; j += 4) acc = fma(ar[j], v[k + 1 + j], acc);
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (row < m && q == 0) pv[k + 1 + row] = tau * acc;
+      // (a2) p = tau * A v; v is zero up to column k, so no column masking is needed; rows <= k give p = 0 below
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+      for (int jj = 0; jj < kEigCols; jj += 4) {
+        acc0 = fma(a[jj], vwk[4 * jj + q].x, acc0);
+        acc1 = fma(a[jj + 1], vwk[4 * (jj + 1) + q].x, acc1);
+        acc2 = fma(a[jj + 2], vwk[4 * (jj + 2) + q].x, acc2);
+        acc3 = fma(a[jj + 3], vwk[4 * (jj + 3) + q].x, acc3);
       }
+      double acc = (acc0 + acc1) + (acc2 + acc3);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (q == 0) pv[row] = (row > k && row < d) ? tau * acc : 0.0;
       __syncthreads();
-      // (a3) K = -tau/2 (p . v), w = p + K v (every warp recomputes K: no extra sync); A22 -= v w^T + w v^T
+      // (a3) K = -tau/2 (p . v) (every warp recomputes it), w = p + K v
       double dot = 0.0;
-      for (int i = lane; i < m; i += 32) dot = fma(pv[k + 1 + i], v[k + 1 + i], dot);
+#pragma unroll
+      for (int u = 0; u < kMaxD / 32; ++u) dot = fma(pv[lane + 32 * u], vwk[lane + 32 * u].x, dot);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       const double K = -0.5 * tau * dot;
-      {
-        const int row = tid >> 2, q = tid & 3;
-        if (row < m) {
-          const double vi = v[k + 1 + row], wi = fma(K, vi, pv[k + 1 + row]);
-          double* ar = A + (k + 1 + row) * pitch + k + 1;
-          for (int j = q; j < m; j += 4) {
-            const double vj = v[k + 1 + j], wj = fma(K, vj, pv[k + 1 + j]);
-            ar[j] -= fma(vi, wj, wi * vj);
-          }
-        }
+      if (q == 0) vwk[row].y = fma(K, vwk[row].x, pv[row]);
+      __syncthreads();
+      // (a4) A -= v w^T + w v^T: rows and columns up to k have v = w = 0 and keep their values
+      const double2 mine = vwk[row];
+#pragma unroll
+      for (int jj = 0; jj < kEigCols; ++jj) {
+        const double2 o = vwk[4 * jj + q];
+        a[jj] = fma(-mine.x, o.y, fma(-mine.y, o.x, a[jj]));
       }
     }
-    __syncthreads();
   }
+  // the last 2 x 2 block comes from the registers of rows d-2, d-1
+  __syncthreads();
+  if (row < d && row + 2 >= d) {
+#pragma unroll
+    for (int jj = 0; jj < kEigCols; ++jj) {
+      const int j = 4 * jj + q;
+      if (j < d && j + 2 >= d) A[row * pitch + j] = a[jj];
+    }
+  }
+  __syncthreads();
+  const int dp8 = (d + 7) & ~7;
   if (tid == 0) {
     if (d >= 2) { dd[d - 2] = A[(d - 2) * pitch + d - 2]; ee2[d - 2] = A[(d - 1) * pitch + d - 2] * A[(d - 1) * pitch + d - 2]; }
     dd[d - 1] = A[(d - 1) * pitch + d - 1];
@@ -530,11 +649,14 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
   }
   __syncthreads();
   const double sdown = misc[2], sup = misc[3];
-  for (int i = tid; i < d; i += blockDim.x) { dd[i] *= sdown; if (i + 1 < d) ee2[i] *= sdown * sdown; }
+  for (int i = tid; i < dp8; i += blockDim.x) {
+    if (i < d) { dd[i] *= sdown; ee2[i] = (i + 1 < d) ? ee2[i] * sdown * sdown : 0.0; }
+    else { dd[i] = 8.0; ee2[i] = 0.0; }                 // padding rows: decoupled, above every scaled eigenvalue (|x| <= 1)
+  }
   __syncthreads();
   // (b) multisection: quad (4 consecutive lanes) owns eigenvalue index e; bracket invariant count(lo) <= e < count(hi)
   for (int e0 = 0; e0 < d; e0 += kEigThreads / 4) {
-    const int e = e0 + (tid >> 2), q = tid & 3;
+    const int e = e0 + (tid >> 2);
     const bool live = e < d;
     double lo = misc[4] * sdown, hi = misc[5] * sdown;
     const double w0 = hi - lo;
@@ -542,14 +664,14 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     for (int round = 0; round < 26; ++round) {
       const double step = (hi - lo) * 0.2;
       const double x = lo + step * (double)(q + 1);
-      const int c = live ? sturm_count(dd, ee2, d, x) : 0;
+      const int c = live ? sturm_count(dd, ee2, dp8, x) : 0;
       const bool below = c <= e;                       // x is still a lower bound of eigenvalue e
       // the 4 points are increasing in q: new lo = the last `below` point, new hi = the first non-`below` point
       const unsigned int quad_shift = (unsigned int)(lane & ~3);
       const unsigned int bal = (__ballot_sync(0xffffffffu, below) >> quad_shift) & 0xFu;
-      const int nb = __popc(bal);                      // below is monotone in x: the first nb points are lower bounds
-      const double nlo = nb > 0 ? lo + step * (double)nb : lo;
-      const double nhi = nb < 4 ? lo + step * (double)(nb + 1) : hi;
+      const int nbel = __popc(bal);                    // below is monotone in x: the first nbel points are lower bounds
+      const double nlo = nbel > 0 ? lo + step * (double)nbel : lo;
+      const double nhi = nbel < 4 ? lo + step * (double)(nbel + 1) : hi;
       lo = nlo; hi = nhi;
     }
     if (live && q == 0) lam[e] = 0.5 * (lo + hi) * sup;
@@ -577,7 +699,10 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
 }
 
 size_t solve_smem_bytes(int d) {
-  return sizeof(double) * ((size_t)(d + 1) * (d + 1) + 3 * d + 16 + (size_t)(d + 1) * kUPitch + 8 * d);
+  // Cholesky: A, mean, invd, misc, U panel; eigenvalue kernel: A, r, mean, misc, (v, w) x 2, pv, dd, ee2, lam
+  const size_t chol = (size_t)(d + 1) * (d + 1) + 3 * d + 16 + (size_t)(d + 1) * kUPitch;
+  const size_t eig = (size_t)(d + 1) * (d + 1) + 3 * d + 16 + 4 * kMaxD + kMaxD + 2 * (kMaxD + 8) + kMaxD;
+  return sizeof(double) * (chol > eig ? chol : eig);
 }
 
 int ensure_solve_attrs(b2_ctx* ctx) {

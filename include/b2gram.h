@@ -82,6 +82,8 @@ int b2_ctx_info(b2_ctx* ctx, char* name, int name_cap, int* sm_count, size_t* hb
 int b2_ctx_set_kernel(b2_ctx* ctx, int kernel);
 /* rows of fp32 tensor-core accumulation before a TMEM drain into fp64 (default 8192) */
 int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows);
+/* the persistent Gram kernel uses at most n_sms SMs (0 = all): leaves room for other work on the device */
+int b2_ctx_set_sm_limit(b2_ctx* ctx, int n_sms);
 /* B2_PRECISION_*: operand precision of the tensor-core path (the CUDA-core kernel is always exact) */
 int b2_ctx_set_precision(b2_ctx* ctx, int precision);
 
@@ -114,9 +116,10 @@ int b2_gram_import(b2_ctx* ctx, const double* S_in, int d);
 
 /* ---- the whole fit in one call: LinearRegression(fit_intercept).fit(X, y) / Ridge(alpha) ----------------------
  * reference: stage_1_train_model.py:105-106.  Equivalent to b2_gram_reset + b2_gram_accumulate + b2_gram_allreduce +
- * b2_solve with the same arguments.  Device-resident rows that take the tensor-core kernel run as two launches: the
- * Gram kernel (reduces and folds its own partials, stores S into the peers' exchange slots when a peer exchange is
- * attached) and the solve kernel (sums the peers' slots, factors, writes coef / intercept to the host). */
+ * b2_solve with the same arguments.  Device-resident rows that take the tensor-core kernel skip the memset, the separate
+ * scatter / gather launches and the D2H copy: the finalize kernel behind the Gram kernel folds the partials and stores
+ * S into the peers' exchange slots (when a peer exchange is attached), the solve kernel sums the peers' slots, factors
+ * and writes coef / intercept to the host. */
 int b2_fit(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int64_t n_rows, int d, int64_t ldx,
            int mem_kind, const uint8_t* row_mask, int mask_keep, double alpha, int fit_intercept,
            double* coef, double* intercept);
@@ -203,7 +206,7 @@ int b2_timer_stop(b2_ctx* ctx, double* ms_out);
 int b2_last_kernel_ms(b2_ctx* ctx, double* gram_ms_out, int* launches_out);
 /* total number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int b2_launch_count(b2_ctx* ctx, int64_t* n_out);
-/* out3[0] fits that took the fused two-launch path of b2_fit, [1] peer exchanges started, [2] kernels launched */
+/* out3[0] fits that took the fused path of b2_fit, [1] peer exchanges started, [2] kernels launched */
 int b2_ctx_stats(b2_ctx* ctx, int64_t* out3);
 
 #ifdef __cplusplus
