@@ -235,12 +235,16 @@ def time_fits(ctx, dist, X, y, steps: int, warmup: int, barrier):
     ctx.last_kernel_ms()
     l0 = ctx.launch_count()
     barrier()
+    host_ms = []
     ctx.timer_start()
     for _ in range(steps):
+        t0 = time.perf_counter()
         sol = ctx.fit(X, y)
+        host_ms.append(1e3 * (time.perf_counter() - t0))
     ms = ctx.timer_stop()
     barrier()
     kms, kl = ctx.last_kernel_ms()
+    time_fits.last_host_ms = host_ms
     return max_over_ranks(dist, ms), kms / max(kl, 1), ctx.launch_count() - l0, sol
 
 
@@ -426,6 +430,39 @@ def main() -> None:
                        "r_squared": float(1.0 - st_all[1] / max(st_all[3] - st_all[2] ** 2 / max(st_all[5], 1.0), 1e-300))}
         ctx.set_kernel(b2.KERNEL_TCGEN05)
 
+    # ---- the north-star point (N = 1): 100 M x 128 fp32 on ONE GPU; strong scaling of the same 100 M rows (N > 1) ------
+    north_star = None
+    strong = None
+    if extras and kind == "f32":
+        ns_rows = NORTH_STAR_ROWS // world
+        if world == 1 or ns_rows != rows:
+            Xn, yn = ctx.synth(ns_rows, D, seed=1234, row_offset=rank * ns_rows, kind="f32")
+            ns_ms, ns_kms, _l, ns_sol = time_fits(ctx, dist, Xn, yn, 5, 3, barrier)
+            chk = exact_check(ctx, b2, Xn, yn, D, ns_sol, dist, f"{ns_rows * world} x {D}")
+            rec = {"rows_total": ns_rows * world, "rows_per_gpu": ns_rows, "ms_per_fit": ns_ms / 5,
+                   "fit_rows_per_s": ns_rows * world / (ns_ms / 5) * 1e3, "gram_kernel_ms": ns_kms,
+                   "gram_kernel_frac_of_hbm_peak": ns_rows * 516 / ns_kms / 1e6 / peak,
+                   "whole_fit_frac_of_hbm_peak": ns_rows * 516 / (ns_ms / 5) / 1e6 / peak,
+                   "coef_linf_vs_exact": chk["coef_linf"], "intercept_abs_err_vs_exact": chk["intercept_abs_err"],
+                   "statistic_rel_err": chk["statistic_rel_err"], "rows_in_statistic": chk["rows_in_statistic"],
+                   "exact_kernel_seconds": chk["exact_kernel_seconds"],
+                   "bit_identical_across_ranks": chk.get("bit_identical_across_ranks"),
+                   "coef_head": [float(c) for c in ns_sol[0][:3]], "intercept": float(ns_sol[1]),
+                   "per_fit_host_ms": [round(v, 3) for v in time_fits.last_host_ms]}
+            Xn.free(); yn.free()
+        else:
+            rec = {"rows_total": total_rows, "rows_per_gpu": rows, "ms_per_fit": ms / args.steps,
+                   "fit_rows_per_s": value, "note": "identical to the headline line (100 M rows over 8 GPUs)",
+                   "coef_linf_vs_exact": parity["coef_linf"]}
+        if world == 1:
+            rec["what"] = ("BASELINE.json north_star: >= 70 % of the HBM roofline on the Gram kernel at N = 100 M, "
+                           "D = 128 on 1 B200, coefficient error < 1e-4")
+            north_star = rec
+        else:
+            rec["what"] = (f"SURVEY 8(d) config 3: the SAME 100 M x 128 rows strong-scaled over {world} GPUs "
+                           f"(1 GPU: the `north_star` object of the N = 1 line)")
+            strong = rec
+
     # ---- e2e: the public estimator API with DEFAULT arguments on HOST rows; H2D inside the timed region -------------
     e2e = None
     if not args.no_e2e:
@@ -559,39 +596,6 @@ def main() -> None:
                              f"(stage_1_train_model.py:105-106), all BLAS threads"}
     if dist is not None:
         dist.barrier()
-
-    # ---- the north-star point (N = 1): 100 M x 128 fp32 on ONE GPU; strong scaling of the same 100 M rows (N > 1) ------
-    north_star = None
-    strong = None
-    if extras and kind == "f32":
-        ns_rows = NORTH_STAR_ROWS // world
-        if world == 1 or ns_rows != rows:
-            X.free(); y.free()
-            Xn, yn = ctx.synth(ns_rows, D, seed=1234, row_offset=rank * ns_rows, kind="f32")
-            ns_ms, ns_kms, _l, ns_sol = time_fits(ctx, dist, Xn, yn, 5, 3, barrier)
-            chk = exact_check(ctx, b2, Xn, yn, D, ns_sol, dist, f"{ns_rows * world} x {D}")
-            rec = {"rows_total": ns_rows * world, "rows_per_gpu": ns_rows, "ms_per_fit": ns_ms / 5,
-                   "fit_rows_per_s": ns_rows * world / (ns_ms / 5) * 1e3, "gram_kernel_ms": ns_kms,
-                   "gram_kernel_frac_of_hbm_peak": ns_rows * 516 / ns_kms / 1e6 / peak,
-                   "whole_fit_frac_of_hbm_peak": ns_rows * 516 / (ns_ms / 5) / 1e6 / peak,
-                   "coef_linf_vs_exact": chk["coef_linf"], "intercept_abs_err_vs_exact": chk["intercept_abs_err"],
-                   "statistic_rel_err": chk["statistic_rel_err"], "rows_in_statistic": chk["rows_in_statistic"],
-                   "exact_kernel_seconds": chk["exact_kernel_seconds"],
-                   "bit_identical_across_ranks": chk.get("bit_identical_across_ranks"),
-                   "coef_head": [float(c) for c in ns_sol[0][:3]], "intercept": float(ns_sol[1])}
-            Xn.free(); yn.free()
-        else:
-            rec = {"rows_total": total_rows, "rows_per_gpu": rows, "ms_per_fit": ms / args.steps,
-                   "fit_rows_per_s": value, "note": "identical to the headline line (100 M rows over 8 GPUs)",
-                   "coef_linf_vs_exact": parity["coef_linf"]}
-        if world == 1:
-            rec["what"] = ("BASELINE.json north_star: >= 70 % of the HBM roofline on the Gram kernel at N = 100 M, "
-                           "D = 128 on 1 B200, coefficient error < 1e-4")
-            north_star = rec
-        else:
-            rec["what"] = (f"SURVEY 8(d) config 3: the SAME 100 M x 128 rows strong-scaled over {world} GPUs "
-                           f"(1 GPU: the `north_star` object of the N = 1 line)")
-            strong = rec
 
     if rank == 0:
         out = {
