@@ -52,6 +52,7 @@ _SIGNATURES = {
     "b2_gram_allreduce": (C.c_int, [_vp]),
     "b2_gram_export": (C.c_int, [_vp, _vp, C.POINTER(_c_i64)]),
     "b2_gram_import": (C.c_int, [_vp, _vp, C.c_int]),
+    "b2_split_mask": (C.c_int, [_c_i64, _c_i64, C.c_uint32, _vp]),
     "b2_fit": (C.c_int, [_vp, _vp, C.c_int, _vp, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp,
                          C.POINTER(C.c_double)]),
     "b2_solve": (C.c_int, [_vp, C.c_double, C.c_int, _vp, C.POINTER(C.c_double)]),

@@ -7,6 +7,8 @@
 #include <stdlib.h>
 
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "b2_internal.cuh"
 #include "b2_xchg.cuh"
@@ -141,11 +143,56 @@ int ensure_staging(b2_ctx* ctx) {
   return B2_OK;
 }
 
+// Is a host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Pageable rows -- what numpy / pandas hand over --
+// cannot be DMA'ed directly: the driver bounces them through one internal staging buffer on one thread (~11 GB/s
+// measured here).  They take the library's own bounce ring instead: several host threads copy the next block into a
+// pinned buffer while the previous block is on the wire.
+bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+int ensure_bounce(b2_ctx* ctx) {
+  if (ctx->bounce[0] != nullptr) return B2_OK;
+  for (int b = 0; b < 2; ++b) {
+    B2_CUDA(cudaHostAlloc(&ctx->bounce[b], ctx->stage_bytes_x, cudaHostAllocDefault));
+    B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_bounce[b], cudaEventDisableTiming));
+  }
+  return B2_OK;
+}
+
+void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)(hw == 0 ? 4 : (hw > 8 ? 8 : hw));
+  if ((size_t)rows * row_bytes < ((size_t)8 << 20)) nt = 1;
+  auto work = [=](int t) {
+    const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
+    if (src_pitch == row_bytes) {
+      memcpy(dst + (size_t)lo * row_bytes, src + (size_t)lo * src_pitch, (size_t)(hi - lo) * row_bytes);
+    } else {
+      for (int64_t r = lo; r < hi; ++r) memcpy(dst + (size_t)r * row_bytes, src + (size_t)r * src_pitch, row_bytes);
+    }
+  };
+  if (nt == 1) { work(0); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+}
+
 // copy rows [r0, r0+rows) of a host matrix into a compact (ldx == d) staging block
 int stage_rows_h2d(b2_ctx* ctx, int buf, const void* X, int es, const float* y, const uint8_t* mask, int64_t r0,
-                   int64_t rows, int d, int64_t ldx) {
+                   int64_t rows, int d, int64_t ldx, bool pinned) {
   const char* src = static_cast<const char*>(X) + (size_t)r0 * ldx * es;
-  if (ldx == d) {
+  if (!pinned) {
+    if (int r = ensure_bounce(ctx)) return r;
+    B2_CUDA(cudaEventSynchronize(ctx->ev_bounce[buf]));                 // the H2D that last read this bounce block is done
+    parallel_copy_rows(static_cast<char*>(ctx->bounce[buf]), src, rows, (size_t)d * es, (size_t)ldx * es);
+    B2_CUDA(cudaMemcpyAsync(ctx->stage_x[buf], ctx->bounce[buf], (size_t)rows * d * es, cudaMemcpyHostToDevice, ctx->copy_stream));
+    B2_CUDA(cudaEventRecord(ctx->ev_bounce[buf], ctx->copy_stream));
+  } else if (ldx == d) {
     B2_CUDA(cudaMemcpyAsync(ctx->stage_x[buf], src, (size_t)rows * d * es, cudaMemcpyHostToDevice, ctx->copy_stream));
   } else {
     B2_CUDA(cudaMemcpy2DAsync(ctx->stage_x[buf], (size_t)d * es, src, (size_t)ldx * es, (size_t)d * es, rows,
@@ -269,6 +316,10 @@ int b2_ctx_destroy(b2_ctx* ctx) {
   if (ctx->solve_host != nullptr) cudaFreeHost(ctx->solve_host);
   if (ctx->xchg_status_host != nullptr) cudaFreeHost(ctx->xchg_status_host);
   if (ctx->coef_host != nullptr) cudaFreeHost(ctx->coef_host);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->bounce[b] != nullptr) cudaFreeHost(ctx->bounce[b]);
+    if (ctx->ev_bounce[b] != nullptr) cudaEventDestroy(ctx->ev_bounce[b]);
+  }
   for (int b = 0; b < 2; ++b) if (ctx->ev_coef[b]) cudaEventDestroy(ctx->ev_coef[b]);
   for (int b = 0; b < 2; ++b) {
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
@@ -391,12 +442,13 @@ int b2_gram_accumulate(b2_ctx* ctx, const void* X, int x_dtype, const float* y, 
   // host rows: stream blocks through a 2-deep HBM staging ring, copies overlapping the kernels
   if (int r = ensure_staging(ctx)) return r;
   const int es = x_dtype == B2_F32 ? 4 : 2;
+  const bool x_pinned = host_pointer_is_pinned(X);
   int64_t blk = 0;
   int rc = B2_OK;
   auto step = [&](int64_t r0, int buf, int64_t rows) -> int {
     // a kernel of this call -- or of an EARLIER call that returned without a stream sync -- may still read this block
     if (ctx->ev_consumed_valid[buf]) B2_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));
-    if (int r = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx)) return r;
+    if (int r = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx, x_pinned)) return r;
     B2_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
     B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
     if (int r = gram_block(ctx, ctx->stage_x[buf], x_dtype, ctx->stage_y[buf], rows, d, d,
@@ -632,6 +684,7 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
   } else {
     if (int r = ensure_staging(ctx)) return r;
     const int es = x_dtype == B2_F32 ? 4 : 2;
+    const bool x_pinned = host_pointer_is_pinned(X);
     // predictions of a staged block land in a device block of their own (allocated once per context) and are copied
     // back behind the kernel
     float* yhat_dev[2] = {nullptr, nullptr};
@@ -652,7 +705,7 @@ int b2_score(b2_ctx* ctx, const void* X, int x_dtype, int64_t n_rows, int d, int
       const int buf = (int)(blk & 1);
       const int64_t rows = (n_rows - r0 < ctx->stage_rows) ? n_rows - r0 : ctx->stage_rows;
       if (ctx->ev_consumed_valid[buf]) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0);
-      rc = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx);
+      rc = stage_rows_h2d(ctx, buf, X, es, y, row_mask, r0, rows, d, ldx, x_pinned);
       if (rc != B2_OK) break;
       cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream);
       cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0);

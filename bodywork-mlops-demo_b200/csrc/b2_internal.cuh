@@ -97,6 +97,8 @@ struct b2_ctx {
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
   bool ev_consumed_valid[2] = {false, false};   // a kernel of an earlier call may still read stage buffer b
   float* yhat_stage[2] = {nullptr, nullptr};    // prediction staging blocks of the host-streamed b2_score
+  void* bounce[2] = {nullptr, nullptr};         // pinned bounce blocks for pageable host rows (filled by host threads)
+  cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   bool s_zero_pending = false;         // b2_gram_reset is lazy: S is cleared (or overwritten) by the first kernel that adds to it
   // NCCL
   void* comm = nullptr;

@@ -49,7 +49,11 @@ log = logging.getLogger(__name__)
 def main() -> None:
     """Main script to be executed (stage_1_train_model.py:31-36)."""
     data, data_date = download_latest_dataset(BUCKET_DIR)
-    model, metrics = train_model(data)
+    try:
+        model, metrics = train_model(data)
+    finally:
+        if isinstance(data, TrancheRows):
+            data.free()
     persist_model(model, data_date, BUCKET_DIR)
     persist_metrics(metrics, data_date, BUCKET_DIR)
 
@@ -58,8 +62,29 @@ def _date_from_key(key: str) -> date:
     return datetime.strptime(_DATE_RE.findall(key)[0], "%Y-%m-%d").date()
 
 
-def download_latest_dataset(bucket_dir: str) -> Tuple[pd.DataFrame, date]:
-    """All tranches under ``<bucket_dir>/datasets`` concatenated oldest -> newest, and the newest date."""
+class TrancheRows:
+    """The accumulated rows of binary (.b2t) tranches in pinned host memory -- what ``download_latest_dataset``
+    returns instead of a DataFrame when every tranche is binary: the bytes go file -> pinned buffer -> HBM, no pandas
+    object is materialised.  ``train_model`` accepts it in place of the DataFrame."""
+
+    def __init__(self, X: np.ndarray, y: np.ndarray, keep=None):
+        self.X, self.y, self._keep = X, y, keep
+
+    def __len__(self) -> int:
+        return int(self.X.shape[0])
+
+    def free(self) -> None:
+        if self._keep is not None:
+            for p in self._keep:
+                p.free()
+            self._keep = None
+        self.X = self.y = None
+
+
+def download_latest_dataset(bucket_dir: str):
+    """All tranches under ``<bucket_dir>/datasets`` concatenated oldest -> newest, and the newest date
+    (stage_1_train_model.py:39-76).  CSV tranches (the reference's format) give a DataFrame; a bucket of binary
+    ``.b2t`` tranches gives ``TrancheRows`` read straight into pinned memory."""
     folder = os.path.join(bucket_dir, "datasets")
     log.info(f"loading all available training data from {folder}")
     try:
@@ -67,6 +92,10 @@ def download_latest_dataset(bucket_dir: str) -> Tuple[pd.DataFrame, date]:
         if not keys:
             raise FileNotFoundError("no regression-dataset-* tranche found")
         dated = sorted(((k, _date_from_key(k)) for k in keys), key=lambda e: e[1])
+        if all(k.endswith(".b2t") for k, _ in dated):
+            from . import tranche_io
+            X, y, newest, keep = tranche_io.load_all(folder, default_context())
+            return TrancheRows(X, y, keep), newest
         dataset = pd.concat(_read_tranche_frame(os.path.join(folder, k)) for k, _ in dated)
     except OSError as e:
         log.error(e)
@@ -98,18 +127,54 @@ def feature_columns(data: pd.DataFrame) -> List[str]:
 
 
 def split_mask(n: int, test_size: float = 0.2, seed: int = 42) -> np.ndarray:
-    """uint8 per row: 1 = train, 0 = test, 2 = unused -- the membership
+    """uint8 per row: 1 = train, 0 = test -- the membership
     ``train_test_split(X, y, test_size=0.2, random_state=42)`` (stage_1_train_model.py:98-103) draws:
-    ``perm = RandomState(seed).permutation(n)``; test = first ceil(test_size*n), train = next floor((1-test_size)*n)."""
+    ``perm = RandomState(seed).permutation(n)``; test = the first ceil(test_size * n) entries, train = the rest.
+
+    The permutation is MT19937 + a Fisher-Yates shuffle: sequential by construction, O(n) host work whatever the GPU
+    does (the reference does it on the host too).  It stays bit-exact; ``b2_split_mask`` (csrc/split_host.cu) restates
+    numpy's legacy generator and shuffle with the swap partners drawn ahead and prefetched (~10x numpy at 10^8 rows),
+    the mask of an (n, test_size, seed) already drawn is re-read from ``$B2_CACHE_DIR`` when that is set, and
+    ``split_mask_async`` runs it beside the host-to-device copy of the rows."""
     n_test = int(np.ceil(test_size * n))
     n_train = n - n_test            # sklearn/model_selection/_split.py: the complement when train_size is None
     if n_train < 1 or n_test < 1:
         raise ValueError(f"With n_samples={n}, test_size={test_size}, the resulting train set will be empty.")
-    perm = np.random.RandomState(seed).permutation(n)
-    mask = np.full(n, 2, dtype=np.uint8)
-    mask[perm[:n_test]] = 0
-    mask[perm[n_test:n_test + n_train]] = 1
+    cache = os.environ.get("B2_CACHE_DIR")
+    path = os.path.join(cache, f"split-mask-n{n}-t{test_size}-s{seed}.u8") if cache else None
+    if path and os.path.exists(path) and os.path.getsize(path) == n:
+        return np.fromfile(path, dtype=np.uint8)
+    mask = np.empty(n, dtype=np.uint8)
+    native._check(native.load().b2_split_mask(n, n_test, int(seed) & 0xFFFFFFFF, mask.ctypes.data), "b2_split_mask")
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        tmp = f"{path}.{os.getpid()}.tmp"
+        mask.tofile(tmp)
+        os.replace(tmp, path)
     return mask
+
+
+class split_mask_async:
+    """``split_mask(n)`` on a worker thread (numpy releases the GIL inside the shuffle): started before the rows go to
+    the device, joined when the mask is needed."""
+
+    def __init__(self, n: int, test_size: float = 0.2, seed: int = 42):
+        import threading
+        self._out, self._err = None, None
+
+        def work():
+            try:
+                self._out = split_mask(n, test_size, seed)
+            except Exception as exc:  # noqa: BLE001 - re-raised by result()
+                self._err = exc
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def result(self) -> np.ndarray:
+        self._thread.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
 
 
 def metrics_from_stats(stats: np.ndarray) -> Tuple[float, float, float]:
@@ -149,21 +214,28 @@ def train_model(data: pd.DataFrame):
     Numeric contract: the rows are staged as float32 (what the kernels stream; the reference keeps pandas' float64),
     sums, solve, predictions and metric reductions are float64 -- coefficients agree with the reference's to ~1e-6
     relative, metrics to ~1e-7 (asserted against fixtures produced by the unmodified reference)."""
-    cols = feature_columns(data)
-    X = np.ascontiguousarray(data[cols].to_numpy(dtype=np.float32))
-    y = np.ascontiguousarray(data["y"].to_numpy(dtype=np.float32))
+    if isinstance(data, TrancheRows):
+        X, y = data.X, data.y                  # pinned, fp32, straight from the tranche files
+    else:
+        cols = feature_columns(data)
+        X = np.ascontiguousarray(data[cols].to_numpy(dtype=np.float32))
+        y = np.ascontiguousarray(data["y"].to_numpy(dtype=np.float32))
     n = X.shape[0]
-    mask = split_mask(n)
+    mask_job = split_mask_async(n)             # O(n) host shuffle, beside the copies below
 
     ctx = default_context()
-    Xd, yd, md = ctx.to_device(X), ctx.to_device(y), ctx.to_device(mask)
+    Xd = yd = md = None
     try:
+        Xd, yd = ctx.to_device(X), ctx.to_device(y)
+        md = ctx.to_device(mask_job.result())
         reg = B200LinearRegression(fit_intercept=True, ctx=ctx)
         reg.fit(Xd, yd, row_mask=md, mask_keep=1)
         _, stats = ctx.score(Xd, reg.coef_, float(reg.intercept_), y=yd, row_mask=md, mask_keep=0,
                              want_yhat=False)
     finally:
-        Xd.free(); yd.free(); md.free()
+        for a in (Xd, yd, md):
+            if a is not None:
+                a.free()
     return reg.to_sklearn(), _metrics_record(*metrics_from_stats(stats))
 
 

@@ -114,6 +114,13 @@ int b2_gram_allreduce(b2_ctx* ctx);
 int b2_gram_export(b2_ctx* ctx, double* S_out, int64_t* n_rows_out);
 int b2_gram_import(b2_ctx* ctx, const double* S_in, int d);
 
+/* ---- split: the row membership of train_test_split(X, y, test_size, random_state=seed) ---------------------------
+ * reference: stage_1_train_model.py:98-103 -> sklearn ShuffleSplit: perm = RandomState(seed).permutation(n_rows);
+ * test = perm[:n_test], train = the rest.  mask_out[r] = 0 for test rows, 1 for train rows (n_rows bytes, host) --
+ * the row_mask b2_gram_accumulate / b2_fit (keep 1) and b2_score (keep 0) consume.  Host-side by nature (MT19937 +
+ * Fisher-Yates are sequential); bit-exact with numpy's legacy generator, ~10x its speed at 10^8 rows. */
+int b2_split_mask(int64_t n_rows, int64_t n_test, uint32_t seed, uint8_t* mask_out);
+
 /* ---- the whole fit in one call: LinearRegression(fit_intercept).fit(X, y) / Ridge(alpha) ----------------------
  * reference: stage_1_train_model.py:105-106.  Equivalent to b2_gram_reset + b2_gram_accumulate + b2_gram_allreduce +
  * b2_solve with the same arguments.  Device-resident rows that take the tensor-core kernel skip the memset, the separate

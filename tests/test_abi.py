@@ -120,6 +120,25 @@ def test_library_has_blackwell_native_sass():
         assert mnemonic in sass, mnemonic
 
 
+def test_split_mask_restates_numpys_legacy_generator_bit_for_bit():
+    """b2_split_mask (host C: MT19937 + Fisher-Yates with prefetched swap partners) == RandomState(seed).permutation(n)
+    for block boundaries of the generator (624 words), rejection-heavy sizes (just above a power of two) and seeds."""
+    for n, seed in ((2, 42), (3, 42), (624, 42), (625, 42), (1025, 42), (65_537, 42), (200_003, 0), (77_777, 2 ** 31 + 5)):
+        n_test = int(np.ceil(0.2 * n))
+        perm = np.random.RandomState(seed).permutation(n)
+        want = np.ones(n, np.uint8); want[perm[:n_test]] = 0
+        assert np.array_equal(s1.split_mask(n, seed=seed), want), (n, seed)
+    lib = b2.native.load()
+    assert lib.b2_split_mask(0, 0, 42, None) == -1 and "b2_split_mask" in b2.native.last_error()
+
+
+def test_split_mask_cache_round_trip(tmp_path, monkeypatch):
+    monkeypatch.setenv("B2_CACHE_DIR", str(tmp_path))
+    a = s1.split_mask(12_345)
+    assert (tmp_path / "split-mask-n12345-t0.2-s42.u8").stat().st_size == 12_345
+    assert np.array_equal(s1.split_mask(12_345), a) and np.array_equal(s1.split_mask_async(12_345).result(), a)
+
+
 @pytest.mark.parametrize("n", [5, 57, 1440, 10_001])
 def test_split_mask_equals_reference_split(golden_dir, n):
     g = np.load(os.path.join(golden_dir, f"sk_split_n{n}.npz"))

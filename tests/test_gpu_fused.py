@@ -401,6 +401,26 @@ def test_back_to_back_host_streamed_accumulates_do_not_overwrite_a_block_in_use(
     Xp.free(); yp.free()
 
 
+def test_pageable_host_rows_take_the_bounce_ring_and_equal_pinned_rows(ctx):
+    """numpy / pandas rows are pageable: they go through the library's pinned bounce ring (host threads copy block k+1
+    while block k is on the wire) -- same statistic, same predictions as page-locked rows."""
+    rows, d = 2 * (1 << 18) + 4_321, 64                           # three staging blocks
+    X, y = orc.generate_dataset(rows, d, seed=21, dtype=np.float32)
+    mask = (np.arange(rows) % 5 != 0).astype(np.uint8)
+    Xp, yp, mp = ctx.pinned((rows, d), np.float32), ctx.pinned((rows,), np.float32), ctx.pinned((rows,), np.uint8)
+    Xp.array[:] = X; yp.array[:] = y; mp.array[:] = mask
+    c_pin, b_pin = ctx.fit(Xp.array, yp.array, mp.array, 1); S_pin = ctx.gram_export()
+    c_pag, b_pag = ctx.fit(X, y, mask, 1); S_pag = ctx.gram_export()
+    assert np.array_equal(S_pin, S_pag) and np.array_equal(c_pin, c_pag) and b_pin == b_pag
+    ref = _oracle_fit(X, y, mask)
+    assert np.max(np.abs(c_pag - ref["coef"])) < COEF_TOL
+    yh_pag, st_pag = ctx.score(X, c_pag, b_pag, y=y, row_mask=mask, mask_keep=0)
+    yh_pin, st_pin = ctx.score(Xp.array, c_pag, b_pag, y=yp.array, row_mask=mp.array, mask_keep=0)
+    assert np.array_equal(yh_pag, yh_pin) and np.array_equal(st_pag, st_pin)
+    for a in (Xp, yp, mp):
+        a.free()
+
+
 def test_estimators_sharing_a_context_do_not_share_a_statistic(ctx):
     Xa, ya = orc.generate_dataset(6000, 8, seed=1, dtype=np.float32)
     Xb, yb = orc.generate_dataset(5000, 8, seed=2, dtype=np.float32)

@@ -675,10 +675,21 @@ def test_stage_reads_binary_tranches(tmp_path, monkeypatch):
         Xs.append(X); ys.append(y)
     monkeypatch.chdir(tmp_path)
     monkeypatch.setattr(s1, "BUCKET_DIR", str(bucket))
+
+    def no_frames(path):                                   # binary tranches go file -> pinned memory -> HBM
+        raise AssertionError(f"a DataFrame was materialised for {path}")
+    monkeypatch.setattr(s1, "_read_tranche_frame", no_frames)
+    data, day = s1.download_latest_dataset(str(bucket))
+    assert isinstance(data, s1.TrancheRows) and len(data) == 120_000 and str(day) == "2021-05-03"
+    assert data.X.dtype == np.float32 and data.X.flags.c_contiguous
+    data.free()
     assert s1.run() == 0
     model = joblib.load(bucket / "models" / "regressor-2021-05-03.joblib")
     o = orc.train_model(np.concatenate(Xs), np.concatenate(ys))
     assert np.max(np.abs(model.coef_ - o["coef"])) < COEF_TOL and model.n_features_in_ == 16
+    metrics = open(bucket / "model-metrics" / "regressor-2021-05-03.csv").read().splitlines()
+    assert metrics[0] == "date,MAPE,r_squared,max_residual"
+    assert abs(float(metrics[1].split(",")[2]) - o["r_squared"]) < 2e-5
 
 
 # ------------------------------------------------------------------------------------------------
