@@ -601,6 +601,12 @@ int b2_solve_eigvals(b2_ctx* ctx, double cond, int fit_intercept, double* singul
   double info = 0.0;
   if (int r = fetch_solution(ctx, false, nullptr, nullptr, singular, rank, &info)) return r;
   if (n_rows_out != nullptr) *n_rows_out = (int64_t)(ctx->solve_host[kMaxD + 3 + kMaxD] + 0.5);
+#ifdef B2_DEV_KNOBS
+  if (getenv("B2_SOLVE_TIMING")) {
+    const double* t = ctx->solve_host + kMaxD + 3 + kMaxD + 1;
+    fprintf(stderr, "[b2_solve_eigvals] cycles: build %.0f tridiagonalise %.0f scale %.0f multisection %.0f\n", t[0], t[1], t[2], t[3]);
+  }
+#endif
   return B2_OK;
 }
 

@@ -493,6 +493,7 @@ solve_spectral_kernel(const double* __restrict__ S, int d, double cond, int fit_
 //       interior points of its bracket, so every round shrinks every bracket 5x with no block-level synchronisation.
 constexpr int kEigThreads = 512;
 constexpr int kEigCols = kMaxD / 4;      // columns per thread: thread (row, q) keeps A[row][4 jj + q] in registers
+constexpr int kEigRounds = 24;           // 5-section rounds: 5^24 = 6e16 > 2^53 * the 1.002 initial bracket
 
 // number of eigenvalues of T below x = sign changes of p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e_{i-2}^2 p_{i-2}.
 // dp8 = d rounded up to 8; rows d .. dp8-1 are decoupled 1 x 1 blocks far above the spectrum (no sign change).  Unrolled
@@ -510,8 +511,11 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ dd, const 
     for (int u = 0; u < 8; ++u) {
       if (i0 + u > 0) {                                                                 // row 0 is p_1 above
         double pn = fma(dv[u], p, -((u == 0 ? eprev : ev[u - 1]) * pm));
-        if (pn == 0.0) pn = (p < 0.0) ? 1e-300 : -1e-300;                               // a zero counts as a sign change
-        count += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+        // sign change / exact zero on the integer pipe (the fp64 pipe is the bottleneck of this loop): a zero counts
+        // as a sign change and continues as a tiny value of the opposite sign
+        const int hn = __double2hiint(pn), hp = __double2hiint(p);
+        if (((hn & 0x7fffffff) | __double2loint(pn)) == 0) pn = __hiloint2double((~hp & 0x80000000) | 0x01a00000, 0);
+        count += (int)(((unsigned int)(__double2hiint(pn) ^ hp)) >> 31);
         pm = p; p = pn;
       }
     }
@@ -540,7 +544,10 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
   double* ee2 = dd + kMaxD + 8;           // [kMaxD + 8] squared off-diagonal of T
   double* lam = ee2 + kMaxD + 8;          // [kMaxD] eigenvalues, ascending
   const int tid = threadIdx.x, lane = tid & 31;
+  long long tph[4];
+  long long tq = clock64();
   build_normal_equations(S, d, 0.0, fit_intercept, A, r, mean, &misc[0]);
+  tph[0] = clock64() - tq; tq = clock64();
 
   // ---- (a) Householder tridiagonalisation, the matrix in registers: thread (row, q) owns columns j = 4 jj + q ----------
   const int row = tid >> 2, q = tid & 3;
@@ -559,14 +566,15 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     //      x = A[k][k+1 ..]; beta = -sign(x0) |x|, tau = (beta - x0) / beta, v = x / (x0 - beta), v[k+1] = 1
     if (row == k) {
       const unsigned int qmask = 0xFu << (lane & ~3);
-      double s2 = 0.0;
+      double s2p[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int jj = 0; jj < kEigCols; ++jj) {
         const int j = 4 * jj + q;
-        if (j > k + 1) s2 = fma(a[jj], a[jj], s2);
+        if (j > k + 1) s2p[jj & 3] = fma(a[jj], a[jj], s2p[jj & 3]);
         if (j == k + 1) misc[6] = a[jj];
         if (j == k) misc[7] = a[jj];
       }
+      double s2 = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
       s2 += __shfl_xor_sync(qmask, s2, 1);
       s2 += __shfl_xor_sync(qmask, s2, 2);
       __syncwarp(qmask);
@@ -588,40 +596,62 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     __syncthreads();
     const double tau = misc[1];
     if (tau != 0.0) {                     // block-uniform
-      // (a2) p = tau * A v; v is zero up to column k, so no column masking is needed; rows <= k give p = 0 below
-      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      // The fp64 pipe is what this phase runs on (measured: ~16 DFMA / clock / SM), so finished rows and columns are
+      // skipped, not multiplied by zero: a warp whose 8 rows are all <= k does nothing, a 32-column group <= k is
+      // jumped over (warp-uniform tests; the register-resident matrix needs compile-time column indices).
+      const bool warp_live = ((tid >> 5) * 8 + 7) > k;
+      // (a2) p = tau * A v
+      if (warp_live) {
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < kEigCols; jj += 4) {
-        acc0 = fma(a[jj], vwk[4 * jj + q].x, acc0);
-        acc1 = fma(a[jj + 1], vwk[4 * (jj + 1) + q].x, acc1);
-        acc2 = fma(a[jj + 2], vwk[4 * (jj + 2) + q].x, acc2);
-        acc3 = fma(a[jj + 3], vwk[4 * (jj + 3) + q].x, acc3);
+        for (int b = 0; b < kEigCols / 8; ++b) {
+          if (32 * b + 31 > k) {
+#pragma unroll
+            for (int u = 0; u < 8; u += 4) {
+              const int jj = 8 * b + u;
+              acc0 = fma(a[jj], vwk[4 * jj + q].x, acc0);
+              acc1 = fma(a[jj + 1], vwk[4 * (jj + 1) + q].x, acc1);
+              acc2 = fma(a[jj + 2], vwk[4 * (jj + 2) + q].x, acc2);
+              acc3 = fma(a[jj + 3], vwk[4 * (jj + 3) + q].x, acc3);
+            }
+          }
+        }
+        double acc = (acc0 + acc1) + (acc2 + acc3);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (q == 0) pv[row] = (row > k && row < d) ? tau * acc : 0.0;
+      } else if (q == 0) {
+        pv[row] = 0.0;
       }
-      double acc = (acc0 + acc1) + (acc2 + acc3);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (q == 0) pv[row] = (row > k && row < d) ? tau * acc : 0.0;
       __syncthreads();
-      // (a3) K = -tau/2 (p . v) (every warp recomputes it), w = p + K v
+      // (a3) K = -tau/2 (p . v), recomputed by every warp; w = p + K v is formed on the fly in (a4) -- one more FMA per
+      // element, one block barrier and one shared-memory round trip fewer per reflection (the loop is latency bound)
       double dot = 0.0;
 #pragma unroll
       for (int u = 0; u < kMaxD / 32; ++u) dot = fma(pv[lane + 32 * u], vwk[lane + 32 * u].x, dot);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       const double K = -0.5 * tau * dot;
-      if (q == 0) vwk[row].y = fma(K, vwk[row].x, pv[row]);
-      __syncthreads();
       // (a4) A -= v w^T + w v^T: rows and columns up to k have v = w = 0 and keep their values
-      const double2 mine = vwk[row];
+      if (warp_live) {
+        const double vr = vwk[row].x, wr = fma(K, vr, pv[row]);
 #pragma unroll
-      for (int jj = 0; jj < kEigCols; ++jj) {
-        const double2 o = vwk[4 * jj + q];
-        a[jj] = fma(-mine.x, o.y, fma(-mine.y, o.x, a[jj]));
+        for (int b = 0; b < kEigCols / 8; ++b) {
+          if (32 * b + 31 > k) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int jj = 8 * b + u;
+              const double vj = vwk[4 * jj + q].x, wj = fma(K, vj, pv[4 * jj + q]);
+              a[jj] = fma(-vr, wj, fma(-wr, vj, a[jj]));
+            }
+          }
+        }
       }
     }
   }
   // the last 2 x 2 block comes from the registers of rows d-2, d-1
   __syncthreads();
+  tph[1] = clock64() - tq; tq = clock64();
   if (row < d && row + 2 >= d) {
 #pragma unroll
     for (int jj = 0; jj < kEigCols; ++jj) {
@@ -634,12 +664,29 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
   if (tid == 0) {
     if (d >= 2) { dd[d - 2] = A[(d - 2) * pitch + d - 2]; ee2[d - 2] = A[(d - 1) * pitch + d - 2] * A[(d - 1) * pitch + d - 2]; }
     dd[d - 1] = A[(d - 1) * pitch + d - 1];
-    // Gershgorin interval, then a power-of-two scaling so that |d_i - x| <= 2 and e_i^2 <= 1 in the recurrence
-    double glo = dd[0], ghi = dd[0];
-    for (int i = 0; i < d; ++i) {
-      const double rad = (i > 0 ? sqrt(ee2[i - 1]) : 0.0) + (i + 1 < d ? sqrt(ee2[i]) : 0.0);
-      glo = fmin(glo, dd[i] - rad); ghi = fmax(ghi, dd[i] + rad);
+  }
+  __syncthreads();
+  // Gershgorin interval (one row per thread, warp 0..3 then a 4-entry combine), then a power-of-two scaling so that
+  // |d_i - x| <= 2 and e_i^2 <= 1 in the recurrence
+  {
+    double glo = 1e300, ghi = -1e300;
+    if (tid < d) {
+      const double rad = (tid > 0 ? sqrt(ee2[tid - 1]) : 0.0) + (tid + 1 < d ? sqrt(ee2[tid]) : 0.0);
+      glo = dd[tid] - rad; ghi = dd[tid] + rad;
     }
+    if (tid < kMaxD) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
+        ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
+      }
+      if (lane == 0) { pv[2 * (tid >> 5)] = glo; pv[2 * (tid >> 5) + 1] = ghi; }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double glo = pv[0], ghi = pv[1];
+    for (int w = 1; w < kMaxD / 32; ++w) { glo = fmin(glo, pv[2 * w]); ghi = fmax(ghi, pv[2 * w + 1]); }
     const double span = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
     int ex = ((__double2hiint(span) >> 20) & 0x7ff) - 1023 + 1;
     ex = ex > 1000 ? 1000 : (ex < -1000 ? -1000 : ex);
@@ -654,6 +701,7 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     else { dd[i] = 8.0; ee2[i] = 0.0; }                 // padding rows: decoupled, above every scaled eigenvalue (|x| <= 1)
   }
   __syncthreads();
+  tph[2] = clock64() - tq; tq = clock64();
   // (b) multisection: quad (4 consecutive lanes) owns eigenvalue index e; bracket invariant count(lo) <= e < count(hi)
   for (int e0 = 0; e0 < d; e0 += kEigThreads / 4) {
     const int e = e0 + (tid >> 2);
@@ -661,7 +709,7 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     double lo = misc[4] * sdown, hi = misc[5] * sdown;
     const double w0 = hi - lo;
     lo -= 1e-3 * w0 + 1e-300; hi += 1e-3 * w0 + 1e-300;
-    for (int round = 0; round < 26; ++round) {
+    for (int round = 0; round < kEigRounds; ++round) {
       const double step = (hi - lo) * 0.2;
       const double x = lo + step * (double)(q + 1);
       const int c = live ? sturm_count(dd, ee2, dp8, x) : 0;
@@ -677,6 +725,9 @@ solve_eigvals_kernel(const double* S, int d, double cond, int fit_intercept, dou
     if (live && q == 0) lam[e] = 0.5 * (lo + hi) * sup;
   }
   __syncthreads();
+  tph[3] = clock64() - tq;
+  if (tid == 0)
+    for (int k = 0; k < 4; ++k) out[kOutRows + 1 + k] = (double)tph[k];   // phase cycles (development builds print them)
   // singular values descending, rank = #{s > cond * s_max}
   const double lmax = fmax(lam[d - 1], 0.0);
   const double smax = sqrt(lmax);
