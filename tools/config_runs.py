@@ -1,6 +1,6 @@
 """Measure the BASELINE.json configs that are not bench.py's headline line (development / evidence tool).
 
-    python tools/config_runs.py [c3] [c4] [c5] [shapes]  -> gpurun_out/r01_configs.json (one record per config)
+    python tools/config_runs.py [c3] [c4] [c5] [shapes] [refshape] [realmask]  -> gpurun_out/r02_configs.json (one record per config)
 
   c3      configs[2] on ONE GPU: 100 M x 128 fp32 resident in HBM (51.6 GB) -- the north-star target point
   c4      configs[3]: D = 32 rows streamed from pinned host DRAM through the C-ABI (B2_MEM_HOST); 200 M rows
@@ -88,6 +88,14 @@ def c4(ctx):
                               "h2d_gb_per_s": n_1b * (d * 4 + 4) / t_1b / 1e9,
                               "how": "5 passes over a 200 M-row (26.4 GB) pinned ring into one statistic, then one solve",
                               "coef_head": [float(c) for c in coef_1b[:2]]}}
+    m = 20_000_000
+    Xn, yn = np.array(Xp.array[:m]), np.array(yp.array[:m])                  # ordinary (pageable) numpy rows
+    est.fit(Xn, yn, with_spectrum=False)
+    t0 = time.perf_counter()
+    est.fit(Xn, yn, with_spectrum=False)
+    tp = time.perf_counter() - t0
+    r["pageable_rows"] = {"n": m, "seconds": tp, "rows_per_s": m / tp, "h2d_gb_per_s": m * (d * 4 + 4) / tp / 1e9,
+                          "how": "numpy rows (not page-locked): pinned bounce ring filled by 8 host threads"}
     Xp.free(); yp.free()
     out["config4_host_streamed_d32"] = r
     print("c4", r, flush=True)
@@ -100,13 +108,10 @@ def c5(ctx):
         tranches = []
         for day in range(days):
             alpha = 1.0 + 0.5 * np.sin(2.0 * np.pi * 6.0 * day / 364.0)       # stage_3...:33,38 intercept drift
-            if d == 1:                                                        # stage_3...:36-43 on the host, seeded
-                rng = np.random.RandomState(900 + day)
-                Xh = rng.uniform(0.0, 100.0, size=(n, 1))
-                yh = alpha + 0.5 * Xh[:, 0] + 10.0 * rng.normal(0.0, 1.0, size=n)
-                keep = yh >= 0                                                # dataset.query('y >= 0')
-                tranches.append((np.ascontiguousarray(Xh[keep], dtype=np.float32),
-                                 np.ascontiguousarray(yh[keep], dtype=np.float32)))
+            if d == 1:                                   # stage_3...:28-43 on the device: alpha(day), y >= 0 filter
+                Xd, yd, kept = ctx.synth_tranche(n, day + 1, seed=900 + day)
+                tranches.append((Xd.to_host()[:kept].copy(), yd.to_host()[:kept].copy()))
+                Xd.free(); yd.free()
             else:
                 Xd, yd = ctx.synth(n, d, seed=900 + day, alpha=alpha)
                 tranches.append((Xd.to_host(), yd.to_host()))
@@ -158,6 +163,40 @@ def refshape(ctx):
     print("refshape", r, flush=True)
 
 
+def realmask(ctx):
+    """The reference's shape with the REAL train_test_split(random_state=42) membership at 200 M rows: the host-side
+    MT19937 + Fisher-Yates shuffle (b2_split_mask) next to the two GPU passes it feeds."""
+    from bodywork_mlops_demo_b200 import stage_1_train_model as s1
+    n, d = 200_000_000, 1
+    X, y = ctx.synth(n, d, seed=4242)
+    ctx.sync()
+    t0 = time.perf_counter()
+    job = s1.split_mask_async(n)
+    mask_h = job.result()
+    t_mask = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mask = ctx.to_device(mask_h)
+    t_h2d = time.perf_counter() - t0
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    est = b2.B200LinearRegression(ctx=ctx)
+    best_fit, best_score = 1e9, 1e9
+    for _ in range(3):
+        ctx.sync(); ctx.timer_start()
+        est.fit(X, y, row_mask=mask, mask_keep=1, with_spectrum=False)
+        best_fit = min(best_fit, ctx.timer_stop())
+        ctx.sync(); ctx.timer_start()
+        _, stats = ctx.score(X, est.coef_, float(est.intercept_), y=y, row_mask=mask, mask_keep=0, want_yhat=False)
+        best_score = min(best_score, ctx.timer_stop())
+    r = {"n": n, "d": d, "split_mask_host_seconds": t_mask, "mask_h2d_seconds": t_h2d, "fit_ms": best_fit,
+         "score_ms": best_score, "train_rows": float(mask_h.sum()), "test_rows": float(stats[5]),
+         "host_ns_per_row": t_mask / n * 1e9,
+         "note": "the split is sequential host work by definition (bit-exact numpy legacy generator); the two GPU "
+                 "passes over the same rows take milliseconds"}
+    X.free(); y.free(); mask.free()
+    out["reference_shape_200Mx1_real_split"] = r
+    print("realmask", r, flush=True)
+
+
 def shapes(ctx):
     res = []
     for d in (1, 8, 16, 32, 64, 128):
@@ -176,9 +215,9 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4", "c5", "shapes", "refshape"]
     ctx = b2.Context(0)
     for w in which:
-        {"c3": c3, "c4": c4, "c5": c5, "shapes": shapes, "refshape": refshape}[w](ctx)
+        {"c3": c3, "c4": c4, "c5": c5, "shapes": shapes, "refshape": refshape, "realmask": realmask}[w](ctx)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    path = os.path.join(ROOT, "gpurun_out", "r01_configs.json")
+    path = os.path.join(ROOT, "gpurun_out", "r02_configs.json")
     prev = json.load(open(path)) if os.path.exists(path) else {}
     prev.update(out)
     json.dump(prev, open(path, "w"), indent=1)
