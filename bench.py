@@ -531,6 +531,21 @@ def main() -> None:
             Xv.free(); yv.free()
         ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
 
+    # ---- the estimator's DEFAULT fit on the resident shard: coefficients AND singular_ / rank_ (eigenvalue kernel) ----
+    default_fit = None
+    if world == 1 and extras:
+        est_d = b2.B200LinearRegression(ctx=ctx)
+        for _ in range(2):
+            est_d.fit(X, y)
+        ctx.sync(); ctx.timer_start()
+        for _ in range(10):
+            est_d.fit(X, y)
+        dms = ctx.timer_stop() / 10
+        default_fit = {"what": "B200LinearRegression().fit(X_dev, y_dev), default arguments, resident rows: b2_fit + "
+                               "b2_solve_eigvals (singular_, rank_ of the sklearn artefact)",
+                       "ms_per_fit": dms, "rows_per_s": rows / dms * 1e3, "spectrum_ms": dms - ms / args.steps,
+                       "rank_": int(est_d.rank_), "singular_head": [float(v) for v in est_d.singular_[:2]]}
+
     # ---- companion kernel: hold-out scoring + metrics over the same resident rows (stage_1...:107, 79-90) ----------
     companion = None
     if world == 1 and extras:
@@ -606,7 +621,7 @@ def main() -> None:
             "config": workload_config(world, kind, rows), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "oracle_pin": oracle_pin, "exchange": exchange,
             "score_shard": score_shard, "north_star": north_star, "strong_100M": strong, "config1_10Mx128": config1,
-            "companion_score": companion,
+            "companion_score": companion, "default_fit_resident": default_fit,
             "host_wall_ms_per_step": 1e3 * t_host / args.steps,
             "coef_head": [float(c) for c in coef[:3]], "intercept": float(b0),
         }

@@ -367,6 +367,7 @@ int b2_ctx_set_drain_rows(b2_ctx* ctx, int rows) {
 int b2_ctx_set_sm_limit(b2_ctx* ctx, int n_sms) {
   if (ctx == nullptr || n_sms < 0) { set_error("n_sms must be >= 0 (0 = all SMs)"); return B2_E_ARG; }
   ctx->sm_limit = n_sms;
+  ctx->sm_limit_auto = false;
   return B2_OK;
 }
 
@@ -969,7 +970,7 @@ int b2_comm_p2p_attach_local(b2_ctx* ctx, int n_ranks, int rank, b2_ctx* const* 
   // launch needs all of its CTAs resident at once -- leave those SMs free (a test / single-GPU configuration)
   int same_device = 0;
   for (int r = 0; r < n_ranks; ++r) same_device += (r != rank && peers[r]->device == ctx->device) ? 1 : 0;
-  if (same_device > 0 && ctx->sm_limit == 0) ctx->sm_limit = ctx->sm_count - 9 * same_device;
+  if (same_device > 0 && ctx->sm_limit == 0) { ctx->sm_limit = ctx->sm_count - 9 * same_device; ctx->sm_limit_auto = true; }
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
   ctx->p2p_ready = true;
@@ -986,6 +987,7 @@ int b2_comm_p2p_detach(b2_ctx* ctx) {
       if (r != ctx->rank && ctx->xchg_peer[r] != nullptr) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
   for (int r = 0; r < kMaxRanks; ++r) ctx->xchg_peer[r] = nullptr;
   if (ctx->p2p_ready && ctx->comm == nullptr) { ctx->n_ranks = 1; ctx->rank = 0; }
+  if (ctx->sm_limit_auto) { ctx->sm_limit = 0; ctx->sm_limit_auto = false; }
   ctx->p2p_ready = false;
   ctx->p2p_local = false;
   cudaGetLastError();

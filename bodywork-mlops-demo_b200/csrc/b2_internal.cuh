@@ -116,6 +116,7 @@ struct b2_ctx {
   unsigned int* tc_sync = nullptr;     // [0], [1] barrier arrivals, [2] ticket
   int fused_fits = 0;                  // fits that took the fused path (b2_ctx_stats)
   int sm_limit = 0;                    // > 0: persistent kernels use at most this many SMs (b2_ctx_set_sm_limit)
+  bool sm_limit_auto = false;          // the limit was set by b2_comm_p2p_attach_local (contexts sharing a device)
 };
 
 namespace b2 {

@@ -18,7 +18,6 @@
 namespace b2 {
 namespace {
 
-constexpr int kSolveThreads = 256;
 constexpr int kOutIntercept = kMaxD;      // solve_out layout: [0,d) coef | intercept | info | rank | singular[d]
 constexpr int kOutInfo = kMaxD + 1;
 constexpr int kOutRank = kMaxD + 2;

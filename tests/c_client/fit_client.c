@@ -1,8 +1,9 @@
 /* A plain C99 client of the drop-in boundary: nothing but include/b2gram.h and libb2gram.so.
  *
  * It does what the reference's retrain does around its three scikit-learn calls
- * (mlops_simulation/stage_1_train_model.py:93-108): hold rows in ordinary host memory, fit, read the
- * coefficients back -- here through the C-ABI a non-Python caller would bind.  The check value is a
+ * (mlops_simulation/stage_1_train_model.py:93-108): hold rows in ordinary host memory, split, fit, score the
+ * hold-out rows, read the coefficients and metrics back -- here through the C-ABI a non-Python caller would bind
+ * (b2_gram_* + b2_solve, the one-call b2_fit, b2_solve_eigvals, b2_split_mask, b2_score).  The check value is a
  * double-precision normal-equation solve written out below (3 features, so Cramer-free Gaussian elimination).
  *
  * exit 0: fitted coefficients agree to 1e-4;  exit 3: no CUDA device (the library has no CPU path);
@@ -96,6 +97,34 @@ int main(void) {
     printf("coef[%d] = %.9f (want %.9f)\n", j, coef[j], want[j]);
   }
   printf("intercept = %.6f (want %.6f); worst coefficient error %.3g\n", intercept, want_b0, worst);
+  {
+    /* the same fit through the one-call entry point, and the spectrum attributes of the estimator */
+    double coef2[D], b2 = 0.0, sing[D];
+    int rank = 0;
+    int64_t rows = 0;
+    if ((rc = b2_fit(ctx, X, B2_F32, y, N, D, D, B2_MEM_HOST, NULL, 1, 0.0, 1, coef2, &b2)) != B2_OK) goto fail;
+    for (j = 0; j < D; ++j)
+      if (coef2[j] != coef[j]) { fprintf(stderr, "b2_fit differs from the four-call sequence\n"); return 1; }
+    if (b2 != intercept) return 1;
+    if ((rc = b2_solve_eigvals(ctx, 1e-6, 1, sing, &rank, &rows)) != B2_OK) goto fail;
+    printf("rank %d, rows %lld, singular values %.4f .. %.4f\n", rank, (long long)rows, sing[0], sing[D - 1]);
+    if (rank != D || rows != N || !(sing[0] >= sing[D - 1] && sing[D - 1] > 0.0)) return 1;
+  }
+  {
+    /* train_test_split's membership (random_state = 42, test_size = 0.2) as a row mask: masked fit + hold-out metrics */
+    uint8_t* mask = (uint8_t*)malloc(N);
+    double stats[10], coef3[D], b3 = 0.0;
+    int64_t n_test = (N + 4) / 5, k, zeros = 0;
+    if (mask == NULL) return 1;
+    if ((rc = b2_split_mask(N, n_test, 42u, mask)) != B2_OK) goto fail;
+    for (k = 0; k < N; ++k) zeros += mask[k] == 0;
+    if (zeros != n_test) { fprintf(stderr, "split mask holds %lld test rows, want %lld\n", (long long)zeros, (long long)n_test); return 1; }
+    if ((rc = b2_fit(ctx, X, B2_F32, y, N, D, D, B2_MEM_HOST, mask, 1, 0.0, 1, coef3, &b3)) != B2_OK) goto fail;
+    if ((rc = b2_score(ctx, X, B2_F32, N, D, D, B2_MEM_HOST, coef3, b3, y, mask, 0, NULL, stats)) != B2_OK) goto fail;
+    printf("hold-out rows %.0f, MAPE %.5f, max |residual| %.3f\n", stats[5], stats[0] / stats[5], stats[4]);
+    if ((int64_t)stats[5] != n_test) return 1;
+    free(mask);
+  }
   b2_ctx_destroy(ctx);
   free(X);
   free(y);

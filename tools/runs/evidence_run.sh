@@ -1,4 +1,5 @@
 #!/bin/bash
+# gpurun -- "bash tools/runs/evidence_run.sh"
 # evidence run: ncu --set full captures of the final kernels (1 GPU), launch list of the bench step, bench line
 mkdir -p gpurun_out; O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
