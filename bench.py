@@ -358,6 +358,9 @@ def main() -> None:
         ctx.sync()
         if dist is not None:
             dist.barrier()
+            # gloo releases the ranks milliseconds apart, and the first exchange of a timed loop absorbs that skew (a
+            # 5-fit loop showed +70 % at N = 4); an NCCL all-reduce + stream sync aligns them to microseconds
+            ctx.comm_barrier()
 
     rows = args.rows or ROWS_PER_GPU
     kind = args.x_dtype
@@ -437,7 +440,11 @@ def main() -> None:
         ns_rows = NORTH_STAR_ROWS // world
         if world == 1 or ns_rows != rows:
             Xn, yn = ctx.synth(ns_rows, D, seed=1234, row_offset=rank * ns_rows, kind="f32")
+            ns_sampler = ClockSampler(local_rank)
+            if rank == 0:
+                ns_sampler.start()
             ns_ms, ns_kms, _l, ns_sol = time_fits(ctx, dist, Xn, yn, 5, 3, barrier)
+            ns_clocks = ns_sampler.stop() if rank == 0 else None
             chk = exact_check(ctx, b2, Xn, yn, D, ns_sol, dist, f"{ns_rows * world} x {D}")
             rec = {"rows_total": ns_rows * world, "rows_per_gpu": ns_rows, "ms_per_fit": ns_ms / 5,
                    "fit_rows_per_s": ns_rows * world / (ns_ms / 5) * 1e3, "gram_kernel_ms": ns_kms,
@@ -448,7 +455,7 @@ def main() -> None:
                    "exact_kernel_seconds": chk["exact_kernel_seconds"],
                    "bit_identical_across_ranks": chk.get("bit_identical_across_ranks"),
                    "coef_head": [float(c) for c in ns_sol[0][:3]], "intercept": float(ns_sol[1]),
-                   "per_fit_host_ms": [round(v, 3) for v in time_fits.last_host_ms]}
+                   "per_fit_host_ms": [round(v, 3) for v in time_fits.last_host_ms], "clocks": ns_clocks}
             Xn.free(); yn.free()
         else:
             rec = {"rows_total": total_rows, "rows_per_gpu": rows, "ms_per_fit": ms / args.steps,
