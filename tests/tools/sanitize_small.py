@@ -49,4 +49,43 @@ if which in ("all", "packed"):
         print("packed", d, S[d, d], st[5])
         for a in (Xpd, ypd, mpd): a.free()
     ctx.set_kernel(b2.KERNEL_AUTO)
+if which in ("all", "fit"):
+    # round 2: the one-call fit (shift sample, Gram, cooperative finalize, LDL^T solve), the eigenvalue kernel, the
+    # metrics-only narrow scorer, float64 metrics, the device tranche generator
+    ctx.set_kernel(b2.KERNEL_TCGEN05); ctx.set_drain_rows(1024)
+    c, b = ctx.fit(Xd, yd, md, 1)
+    sing, rank, rows = ctx.solve_eigvals()
+    print("fit", c[:2], rank, rows)
+    X3, y3 = orc.generate_dataset(700, 33, seed=2, dtype=np.float32)
+    ctx.set_kernel(b2.KERNEL_AUTO)
+    c3, b3 = ctx.fit(X3, y3); print("fit33 host rows", c3[:2], ctx.solve_eigvals()[1])
+    for d in (1, 2, 8):
+        Xn, yn = orc.generate_dataset(20000 + d, d, seed=30 + d, dtype=np.float32)
+        Xnd, ynd = ctx.to_device(Xn), ctx.to_device(yn)
+        _, st = ctx.score(Xnd, np.full(d, 0.5), 1.0, y=ynd, want_yhat=False)
+        print("score plain", d, st[5]); Xnd.free(); ynd.free()
+    print("metrics", ctx.metrics(y.astype(np.float64), y.astype(np.float64) * 1.01)[5])
+    Xt, yt, kept = ctx.synth_tranche(5000, 7, seed=5); print("tranche", kept); Xt.free(); yt.free()
+if which in ("all", "xchg"):
+    # peer-memory exchange between two contexts on this device: finalize-kernel scatter + solve-kernel gather, and the
+    # stand-alone scatter / gather kernels
+    import threading
+    cs = [ctx, b2.Context(0)]
+    b2.Context.comm_p2p_attach_local(cs)
+    half = len(y) // 2
+    sh = [(cs[0].to_device(X[:half]), cs[0].to_device(y[:half])), (cs[1].to_device(X[half:]), cs[1].to_device(y[half:]))]
+    out = [None, None]
+    for mode in ("fused", "standalone"):
+        def work(i):
+            c = cs[i]
+            c.set_kernel(b2.KERNEL_TCGEN05)
+            if mode == "fused":
+                out[i] = c.fit(sh[i][0], sh[i][1])
+            else:
+                c.gram_reset(128); c.gram_accumulate(sh[i][0], sh[i][1]); c.gram_allreduce(); out[i] = c.solve()
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        [t.start() for t in ts]; [t.join() for t in ts]
+        print("xchg", mode, out[0][0][:2], bool(np.array_equal(out[0][0], out[1][0])), cs[0].gram_export()[128, 128])
+    for c in cs: c.comm_p2p_detach()
+    cs[1].close()
 print("done")
