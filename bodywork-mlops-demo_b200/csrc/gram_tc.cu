@@ -180,23 +180,33 @@ __device__ __forceinline__ float shift_value(const float* __restrict__ sp, int j
   return __bfloat162float(__float2bfloat16_rn(acc / (float)shift_samples(n)));
 }
 
+// 64 blocks x (4 row groups x 160 columns): a thread sums 8 sample rows (one batch of loads in flight -- the rows are
+// megabytes apart, every load is a DRAM round trip), the 4 groups are combined in a fixed order.
+constexpr int kShiftCols = 160;                  // >= kMaxD + 1, a multiple of 32
+constexpr int kShiftGroups = 4;
+
 template <typename T>
-__global__ void tc_shift_kernel(const T* __restrict__ X, const float* __restrict__ y, int64_t n, int d,
-                                int64_t ldx, float* __restrict__ sp) {
-  const int j = threadIdx.x;
-  if (j > d) return;
+__global__ void __launch_bounds__(kShiftCols * kShiftGroups)
+tc_shift_kernel(const T* __restrict__ X, const float* __restrict__ y, int64_t n, int d,
+                int64_t ldx, float* __restrict__ sp) {
+  __shared__ float sub[kShiftGroups][kShiftCols];
+  const int j = threadIdx.x % kShiftCols, g = threadIdx.x / kShiftCols;
   const int64_t samples = shift_samples(n);
   const int64_t stride = n / samples;
   const int64_t per = (samples + kShiftBlocks - 1) / kShiftBlocks;
   const int64_t s0 = blockIdx.x * per;
   const int64_t s1 = (s0 + per < samples) ? s0 + per : samples;
   float acc = 0.f;
+  if (j <= d) {
 #pragma unroll 8
-  for (int64_t s = s0; s < s1; ++s) {
-    const int64_t row = s * stride;
-    acc += (j < d) ? raw_ld_global<T>(X + row * ldx + j) : __ldg(y + row);
+    for (int64_t s = s0 + g; s < s1; s += kShiftGroups) {
+      const int64_t row = s * stride;
+      acc += (j < d) ? raw_ld_global<T>(X + row * ldx + j) : __ldg(y + row);
+    }
   }
-  sp[blockIdx.x * kShiftStride + (j == d ? kMaxD : j)] = acc;
+  sub[g][j] = acc;
+  __syncthreads();
+  if (g == 0 && j <= d) sp[blockIdx.x * kShiftStride + (j == d ? kMaxD : j)] = ((sub[0][j] + sub[1][j]) + sub[2][j]) + sub[3][j];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -702,8 +712,18 @@ tc_finalize_kernel(const double* part, const double* side, int n_ctas, double* r
                    int64_t n_rows, int d, int pack, double* S, unsigned int* sync, const TcFinal fin) {
   __shared__ double quarter[kFinalizeThreads];
   __shared__ double c_s[kMaxD + 1];                              // the shift as fp64 (c_s[kMaxD]: c_y)
-  for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x)
-    c_s[j] = (j < d || j == kMaxD) ? (double)shift_value(shift, j, n_rows) : 0.0;
+  __shared__ float c_part[kShiftBlocks * kShiftStride];          // the 64 partial sums of the shift sample (33 KB)
+  // the same values shift_value() gives the Gram kernel -- same operands, same order of the 64 additions -- but with
+  // all loads of the CTA in flight at once: the serial walk (8 batches of dependent-latency loads by 129 threads while
+  // 895 wait at the next barrier) was 40 % of this kernel (profiles/r02_tc_finalize_summary.txt)
+  for (int idx = threadIdx.x; idx < kShiftBlocks * kShiftStride; idx += blockDim.x) c_part[idx] = __ldg(shift + idx);
+  __syncthreads();
+  for (int j = threadIdx.x; j <= kMaxD; j += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < kShiftBlocks; ++b) acc += c_part[b * kShiftStride + j];
+    c_s[j] = (j < d || j == kMaxD) ? (double)__bfloat162float(__float2bfloat16_rn(acc / (float)shift_samples(n_rows))) : 0.0;
+  }
   {
     constexpr int epb = kFinalizeThreads / 4;                    // elements per pass of a CTA
     const int per = (((kRedElems + (int)gridDim.x - 1) / (int)gridDim.x) + epb - 1) / epb * epb;
@@ -926,10 +946,10 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     if (int r = ensure_s_cleared(ctx)) return r;
   }
   if (x_dtype == B2_F32)
-    tc_shift_kernel<float><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
+    tc_shift_kernel<float><<<kShiftBlocks, kShiftCols * kShiftGroups, 0, ctx->stream>>>(static_cast<const float*>(X), y, n_in, d_in,
                                                                   ldx_in, ctx->shift);
   else
-    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, 160, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
+    tc_shift_kernel<__nv_bfloat16><<<kShiftBlocks, kShiftCols * kShiftGroups, 0, ctx->stream>>>(static_cast<const __nv_bfloat16*>(X), y,
                                                                           n_in, d_in, ldx_in, ctx->shift);
   B2_CUDA(cudaGetLastError());
 
