@@ -683,6 +683,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+#include "gram_tc_b16.cuh"
+
 // ------------------------------------------------------------------------------------------
 // finalize: tc_reduce_kernel sums the per-CTA partials in CTA order (deterministic)
 //   red[col * 128 + i], col in [0, 288):  col < 144: D1 (A = hi), col >= 144: D2 (A = lo), columns of [hi | E]
@@ -788,8 +790,9 @@ bool gram_tc_supported(const void* X, int x_dtype, const float* y, int64_t n, in
 }
 
 // d: inner extent of the (super-)row tensor; d_box: inner extent of the smem tile (> d: the rest is zero fill)
+// swz64: the bf16 D = 128 kernel's raw layout -- [64 rows][64 features] boxes (128-byte rows) with SWIZZLE_128B
 static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int es, const float* y, int64_t n, int d,
-                       int d_box, int64_t ldx, int64_t n_y, int pack, const uint8_t* mask, CUtensorMap* tmX_out,
+                       int d_box, int64_t ldx, int64_t n_y, int pack, const uint8_t* mask, bool swz64, CUtensorMap* tmX_out,
                        CUtensorMap* tmY_out, CUtensorMap* tmM_out, int* y_map_2d_out, int* m_map_2d_out) {
   const cuuint32_t y_box = (cuuint32_t)(kTcRows * pack);   // original rows per tile
   CUtensorMap& tmX = *tmX_out; CUtensorMap& tmY = *tmY_out; CUtensorMap& tmM = *tmM_out;
@@ -797,11 +800,11 @@ static int encode_maps(PFN_encodeTiled encode, const void* X, int x_dtype, int e
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)ldx * es};
-    cuuint32_t box[2] = {(cuuint32_t)d_box, (cuuint32_t)kTcRows};
+    cuuint32_t box[2] = {(cuuint32_t)(swz64 ? 64 : d_box), (cuuint32_t)kTcRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmX, x_dtype == B2_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                         2, const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swz64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(X) failed with %d (n=%lld d=%d box=%d ldx=%lld)", (int)r, (long long)n, d, d_box,
@@ -906,6 +909,10 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   const int d_tensor = d_in * pack;                     // columns that exist; the tile is zero-filled beyond them
   const int64_t ldx = ldx_in * pack;
   const int64_t n_y = n_main;                           // y / mask elements covered by the tensor maps
+  // bf16-stored rows with D = 128 take their own kernel (gram_tc_b16.cuh); B2_TC_B16_GENERIC=1 keeps them on the generic
+  // kernel (diagnostic switch for same-box A/B runs)
+  static const bool b16_generic = []() { const char* e = getenv("B2_TC_B16_GENERIC"); return e != nullptr && e[0] == '1'; }();
+  const bool b16 = x_dtype == B2_BF16 && d_in == 128 && pack == 1 && !b16_generic;
   CUtensorMap tmX, tmY, tmM;
   int y_map_2d = 0, m_map_2d = 0;
   b2_ctx::TmCache& tc = ctx->tm_cache;
@@ -915,7 +922,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     memcpy(&tmX, tc.tmX, sizeof(tmX)); memcpy(&tmY, tc.tmY, sizeof(tmY)); memcpy(&tmM, tc.tmM, sizeof(tmM));
     y_map_2d = tc.y_map_2d & 1; m_map_2d = (tc.y_map_2d >> 1) & 1;
   } else {
-    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d_tensor, d, ldx, n_y, pack, mask, &tmX, &tmY, &tmM, &y_map_2d,
+    if (int r = encode_maps(encode, X, x_dtype, es, y, n, d_tensor, d, ldx, n_y, pack, mask, b16, &tmX, &tmY, &tmM, &y_map_2d,
                             &m_map_2d))
       return r;
     tc.X = X; tc.y = y; tc.mask = mask; tc.n = n_in; tc.ldx = ldx_in; tc.d = d_in; tc.x_dtype = x_dtype;
@@ -937,6 +944,8 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     B2_SET_SMEM(__nv_bfloat16, 128, true); B2_SET_SMEM(__nv_bfloat16, 0, true);
     B2_SET_SMEM(__nv_bfloat16, 128, false); B2_SET_SMEM(__nv_bfloat16, 0, false);
 #undef B2_SET_SMEM
+    B2_CUDA(cudaFuncSetAttribute(b16::gram_b16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmem));
+    B2_CUDA(cudaFuncSetAttribute(b16::gram_b16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmem));
     ctx->tc_attr_set = true;
   }
 
@@ -979,7 +988,15 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
 #define B2_LAUNCH_TC_D(T, SP) \
   do { if (d == 128) B2_LAUNCH_TC(T, 128, SP); else B2_LAUNCH_TC(T, 0, SP); } while (0)
   const bool split = ctx->precision == B2_PRECISION_SPLIT;
-  if (x_dtype == B2_F32) {
+  if (b16) {
+    const int hm = mask != nullptr ? 1 + m_map_2d : 0;
+    if (split)
+      b16::gram_b16_kernel<true><<<grid, kThreads, b16::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in, ctx->shift,
+                                                                              chunk_tiles, ctx->tc_part, ctx->tc_side);
+    else
+      b16::gram_b16_kernel<false><<<grid, kThreads, b16::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in, ctx->shift,
+                                                                               chunk_tiles, ctx->tc_part, ctx->tc_side);
+  } else if (x_dtype == B2_F32) {
     if (split) B2_LAUNCH_TC_D(float, true); else B2_LAUNCH_TC_D(float, false);
   } else {
     if (split) B2_LAUNCH_TC_D(__nv_bfloat16, true); else B2_LAUNCH_TC_D(__nv_bfloat16, false);
