@@ -69,6 +69,15 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "r"(tmem_a), "l"(bdesc), "r"(id), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp.  ptxas treats a region guarded by elect.sync as single-threaded: the tcgen05.mma / TMA
+// instructions inside compile to back-to-back uniform-datapath instructions with their operands in uniform registers.
+// Guarded by `lane == 0` instead, every one of them is wrapped in an ELECT / BRA.U.ANY waterfall loop behind a chain of
+// R2UR moves, and the issue of one MMA costs ~150 cycles -- which made the MMA-issuing thread the bound of this kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -198,13 +207,13 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const uint32_t tx = kRawBytes + kTcRows * 4 + (has_mask ? kTcRows : 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        wait_lean(bar_raw_empty + 8 * s, ph ^ 1);
+    // ===== TMA producer (the whole warp runs the loop, one elected lane issues) =====
+    const uint32_t tx = kRawBytes + kTcRows * 4 + (has_mask ? kTcRows : 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      wait_lean(bar_raw_empty + 8 * s, ph ^ 1);
+      if (elect_one()) {
         const uint32_t full = bar_raw_full + 8 * s;
         mbar_expect_tx(full, tx);
         const int row0 = (int)((tile_begin + it) * kTcRows);
@@ -214,40 +223,42 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         else tma_load_1d(sbase + kOffY + s * kYBytes, &tmY, row0, full);
         if (has_mask == 2) tma_load_2d(sbase + kOffMask + s * kMBytes, &tmM, 0, row0 >> 4, full);
         else if (has_mask) tma_load_1d(sbase + kOffMask + s * kMBytes, &tmM, row0, full);
-        if (++s == kRaw) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == kRaw) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      int os = 0;
-      uint32_t oph = 0;
-      int in_chunk = 0, chunk = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int b = chunk & 1;
-        if (in_chunk == 0) {
-          wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
-        wait_lean(bar_op_full + 8 * os, oph);
-        tc_fence_after();
+    // ===== MMA issuer (the whole warp runs the loop, one elected lane issues) =====
+    int os = 0;
+    uint32_t oph = 0;
+    int in_chunk = 0, chunk = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int b = chunk & 1;
+      if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
+      wait_lean(bar_op_full + 8 * os, oph);
+      tc_fence_after();
+      const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
+      if (elect_one()) {
         const uint32_t op_addr = sbase + kOffOp + os * kOpBytes;
         const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
+        // descriptors of consecutive K steps differ by a constant in the address field (no carry: smem addresses < 2^18)
+        const uint64_t desc_e = make_smem_desc(op_addr, kLBO), desc_hi = make_smem_desc(op_addr + kHiOff, kLBO);
 #pragma unroll
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint32_t kg = op_addr + k2 * 2 * kLBO;
-          umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), make_smem_desc(kg + kHiOff, kLBO),
-                  idesc(144), (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                  // [G | Eb] += hi^T [hi | E]
+          const uint64_t step = (uint64_t)((k2 * 2 * kLBO) >> 4);
+          umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi + step, idesc(144),
+                  (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                             // [G | Eb] += hi^T [hi | E]
           if constexpr (SPLIT)
-            umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), make_smem_desc(kg, kLBO), idesc(144),
-                    1u);                                                                            // [Ea | G] += 2 lo^T [E | hi]
+            umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e + step, idesc(144), 1u);
+                                                                                                    // [Ea | G] += 2 lo^T [E | hi]
         }
         umma_commit(bar_op_empty + 8 * os);
-        const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
-        if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
-        else ++in_chunk;
-        if (++os == kOps) { os = 0; oph ^= 1; }
+        if (last) umma_commit(bar_acc_full + 8 * b);
       }
+      __syncwarp();
+      if (last) { in_chunk = 0; ++chunk; }
+      else ++in_chunk;
+      if (++os == kOps) { os = 0; oph ^= 1; }
     }
   } else if (warp == 2 || warp == 3) {
     // ===== E warps: operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' (one row per lane) =====
