@@ -32,7 +32,8 @@
 namespace b16 {
 
 constexpr int kRaw = 6;                                   // raw tile stages (16 KB each)
-constexpr int kOps = 3;                                   // operand stages: smem B ring and the tensor-memory A rings
+constexpr int kOpsMax = 4;                                // operand stages (smem B ring + tensor-memory A rings): 3 with two A
+                                                          // operands (192 tensor-memory columns), 4 in single-operand mode
 constexpr uint32_t kRawBytes = kTcRows * 128 * 2;         // 16384
 constexpr uint32_t kRawHalf = kTcRows * 128;              // 8192: one [64][64] bf16 box
 constexpr uint32_t kLBO = (2 + 16 + 2) * kOpSBO;          // 2560: E | hi | E groups per 8-row K group
@@ -41,12 +42,12 @@ constexpr uint32_t kE1Off = (2 + 16) * kOpSBO;            // the E copy behind h
 constexpr uint32_t kOpBytes = kKGroups * kLBO;            // 20480
 constexpr uint32_t kOffRaw = 0;
 constexpr uint32_t kOffOp = kOffRaw + kRaw * kRawBytes;   // 98304
-constexpr uint32_t kOffY = kOffOp + kOps * kOpBytes;      // 159744
+constexpr uint32_t kOffY = kOffOp + kOpsMax * kOpBytes;   // 180224
 constexpr uint32_t kYBytes = kTcRows * 4;                 // 256
 constexpr uint32_t kMBytes = 128;                         // 64 mask bytes, padded (TMA destinations are 128-byte aligned)
 constexpr uint32_t kOffMask = kOffY + kRaw * kYBytes;
 constexpr uint32_t kOffBar = kOffMask + kRaw * kMBytes;
-constexpr int kBars = 2 * kRaw + 2 * kOps + 4;
+constexpr int kBars = 2 * kRaw + 2 * kOpsMax + 4;
 constexpr uint32_t kOffTmemPtr = kOffBar + kBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
 constexpr uint32_t kSmem = kOffShift + (kMaxD + 4) * 4 + 1024;
@@ -143,6 +144,7 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep, int64_t n_rows,
                 int64_t n_shift, const float* __restrict__ shift, int chunk_tiles, double* __restrict__ part,
                 double* __restrict__ side) {
+  constexpr int kOps = SPLIT ? 3 : kOpsMax;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -152,8 +154,8 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t bar_raw_full = sbase + kOffBar;                 // [kRaw]
   const uint32_t bar_raw_empty = bar_raw_full + 8 * kRaw;        // [kRaw]
   const uint32_t bar_op_full = bar_raw_empty + 8 * kRaw;         // [kOps]
-  const uint32_t bar_op_empty = bar_op_full + 8 * kOps;          // [kOps]
-  const uint32_t bar_acc_full = bar_op_empty + 8 * kOps;         // [2]
+  const uint32_t bar_op_empty = bar_op_full + 8 * kOpsMax;       // [kOps]
+  const uint32_t bar_acc_full = bar_op_empty + 8 * kOpsMax;      // [2]
   const uint32_t bar_acc_empty = bar_acc_full + 16;              // [2]
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
   float* shift_s = reinterpret_cast<float*>(smem + kOffShift);
@@ -189,7 +191,7 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // the unused E rows of the operand stages read as 0
-  for (uint32_t o = threadIdx.x * 16; o < kOps * kOpBytes; o += kThreads * 16)
+  for (uint32_t o = threadIdx.x * 16; o < kOpsMax * kOpBytes; o += kThreads * 16)
     *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
   for (int j = threadIdx.x; j <= kMaxD; j += kThreads) shift_s[j] = shift_value(shift, j, n_shift);
   fence_proxy_async_smem();
