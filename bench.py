@@ -522,7 +522,10 @@ def main() -> None:
     # ---- BASELINE configs[1]: 10 M x 128 on one GPU, every storage x operand combination ---------------------------
     config1 = None
     if world == 1 and extras:
-        config1 = {"what": "BASELINE.json configs[1]: 10 M x 128 rows resident on one GPU; complete fits (b2_fit)", "rows": ROWS_CONFIG1}
+        config1 = {"what": "BASELINE.json configs[1]: 10 M x 128 rows resident on one GPU; complete fits (b2_fit); bf16-stored "
+                           "rows run gram_b16_kernel; coef_linf_vs_exact: against the exact fp64 kernel over the same stored rows",
+                   "rows": ROWS_CONFIG1}
+        exact_c1 = {}
         for vk, vprec in (("f32", "split"), ("f32", "bf16"), ("bf16", "split"), ("bf16", "bf16")):
             Xv, yv = ctx.synth(ROWS_CONFIG1, D, seed=1234, kind=vk)
             ctx.set_precision(b2.PRECISION_BF16 if vprec == "bf16" else b2.PRECISION_SPLIT)
@@ -535,6 +538,13 @@ def main() -> None:
                 "mma_tflops_issued": ROWS_CONFIG1 * mma / vk_ms / 1e9,
                 "frac_of_bf16_tensor_peak": ROWS_CONFIG1 * mma / vk_ms / 1e9 / measured_tensor_peak(),
                 "coef_head": [float(c) for c in vsol[0][:2]]}
+            if vk not in exact_c1:          # the exact fp64 kernel over the same stored rows, once per storage type
+                ctx.set_kernel(b2.KERNEL_SIMT)
+                ctx.gram_reset(D); ctx.gram_accumulate(Xv, yv)
+                exact_c1[vk] = ctx.solve()[0]
+                ctx.set_kernel(b2.KERNEL_TCGEN05)
+            config1[f"x_{vk}_operands_{'bf16x1' if vprec == 'bf16' else 'bf16x2'}"]["coef_linf_vs_exact"] = \
+                float(np.max(np.abs(vsol[0] - exact_c1[vk])))
             Xv.free(); yv.free()
         ctx.set_precision(b2.PRECISION_BF16 if args.precision == "bf16" else b2.PRECISION_SPLIT)
 

@@ -118,6 +118,10 @@ def test_library_has_blackwell_native_sass():
     # (gram_narrow, score kernels), mbarrier try_wait pipelines
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UBLKCP", "FFMA2", "SYNCS.PHASECHK.TRANS64.TRYWAIT"):
         assert mnemonic in sass, mnemonic
+    # the bf16-storage kernel (gram_tc_b16.cuh): transposing ldmatrix, 16-lane tensor-memory stores that take the ldmatrix
+    # fragments as they are, packed bf16 subtract, mixed-precision bf16 x bf16 + fp32 FMA
+    for mnemonic in ("LDSM.16.MT88.4", "STTM.16dp128bit.x2", "HFMA2.BF16_V2", "FHFMA.BF16"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_split_mask_restates_numpys_legacy_generator_bit_for_bit():

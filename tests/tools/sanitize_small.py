@@ -66,6 +66,20 @@ if which in ("all", "fit"):
         print("score plain", d, st[5]); Xnd.free(); ynd.free()
     print("metrics", ctx.metrics(y.astype(np.float64), y.astype(np.float64) * 1.01)[5])
     Xt, yt, kept = ctx.synth_tranche(5000, 7, seed=5); print("tranche", kept); Xt.free(); yt.free()
+if which in ("all", "b16"):
+    # bf16-stored rows, D = 128: gram_b16_kernel (ldmatrix.trans, tcgen05.st.16x128b, merged accumulator), both operand
+    # modes, with a mask and a ragged last tile, short drain interval
+    Xb = b2.native.to_bf16_bits(X)
+    Xbd = ctx.to_device(Xb, "bf16")
+    ctx.set_kernel(b2.KERNEL_TCGEN05); ctx.set_drain_rows(1024)
+    for prec in (b2.PRECISION_SPLIT, b2.PRECISION_BF16):
+        ctx.set_precision(prec)
+        ctx.gram_reset(128); ctx.gram_accumulate(Xbd, yd, md, 1)
+        print("b16 masked n", ctx.gram_export()[128, 128])
+        c, b = ctx.fit(Xbd, yd)
+        print("b16 fit", c[:2])
+    ctx.set_precision(b2.PRECISION_SPLIT); ctx.set_drain_rows(8192); ctx.set_kernel(b2.KERNEL_AUTO)
+    Xbd.free()
 if which in ("all", "xchg"):
     # peer-memory exchange between two contexts on this device: finalize-kernel scatter + solve-kernel gather, and the
     # stand-alone scatter / gather kernels

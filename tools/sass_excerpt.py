@@ -5,11 +5,11 @@ SO = "bodywork-mlops-demo_b200/libb2gram.so"
 sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
 print(f"# cuobjdump -sass {SO}  ({datetime.datetime.utcnow():%Y-%m-%dT%H:%MZ})")
 print("# mnemonic counts over the whole library (B200_PROFILING.md: UTC*MMA = tcgen05.mma, UTMALDG / UBLKCP = TMA, LDTM / STTM = tcgen05.ld / st)")
-for m in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "STTM", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "FFMA2", "DMMA", "MUFU.RCP64H", "MEMBAR.SC.SYS", "NANOSLEEP"):
+for m in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "STTM", "LDSM", "FHFMA.BF16", "HFMA2.BF16_V2", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "FFMA2", "DMMA", "MUFU.RCP64H", "MEMBAR.SC.SYS", "NANOSLEEP"):
     print(f"{m:34s} {sass.count(m)}")
 funcs = re.split(r"(?=\s+Function : )", sass)
-WANT = r"UTCHMMA|UTMALDG|UBLKCP|LDTM|STTM|UTCBAR|SYNCS\.|DMMA|MUFU\.RCP64H|FFMA2|\.SYS|MEMBAR|ATOMG|REDG|NANOSLEEP|UTCATOM|DFMA|LDS\.128|STS\.128|BAR\.SYNC|ST\.E|LDG"
-for pat in ("gram_tc_kernelIfLi128ELb1", "tc_finalize_kernel", "solve_cholesky_kernel", "solve_eigvals_kernel",
+WANT = r"LDSM|FHFMA|HFMA2\.BF16|HADD2\.BF16|ELECT|UTCHMMA|UTMALDG|UBLKCP|LDTM|STTM|UTCBAR|SYNCS\.|DMMA|MUFU\.RCP64H|FFMA2|\.SYS|MEMBAR|ATOMG|REDG|NANOSLEEP|UTCATOM|DFMA|LDS\.128|STS\.128|BAR\.SYNC|ST\.E|LDG"
+for pat in ("gram_tc_kernelIfLi128ELb1", "gram_b16_kernelILb1", "gram_b16_kernelILb0", "tc_shift_kernelIf", "tc_finalize_kernel", "solve_cholesky_kernel", "solve_eigvals_kernel",
             "score_narrow_kernelIfLi1ELb1ELb1", "gram_narrow_kernelIfLi8", "p2p_scatter_kernel", "p2p_gather_kernel"):
     body = next((f for f in funcs if re.search(r"Function : \S*" + pat, f)), None)
     if body is None:
