@@ -684,6 +684,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 #include "gram_tc_b16.cuh"
+#include "gram_tc_b16_split.cuh"
 
 // ------------------------------------------------------------------------------------------
 // finalize: tc_reduce_kernel sums the per-CTA partials in CTA order (deterministic)
@@ -909,7 +910,7 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   const int d_tensor = d_in * pack;                     // columns that exist; the tile is zero-filled beyond them
   const int64_t ldx = ldx_in * pack;
   const int64_t n_y = n_main;                           // y / mask elements covered by the tensor maps
-  // bf16-stored rows with D = 128 take their own kernel (gram_tc_b16.cuh); B2_TC_B16_GENERIC=1 keeps them on the generic
+  // bf16-stored rows with D = 128 take their own kernels (gram_tc_b16.cuh: single operand, gram_tc_b16_split.cuh: hi + lo); B2_TC_B16_GENERIC=1 keeps them on the generic
   // kernel (diagnostic switch for same-box A/B runs)
   static const bool b16_generic = []() { const char* e = getenv("B2_TC_B16_GENERIC"); return e != nullptr && e[0] == '1'; }();
   const bool b16 = x_dtype == B2_BF16 && d_in == 128 && pack == 1 && !b16_generic;
@@ -944,8 +945,8 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
     B2_SET_SMEM(__nv_bfloat16, 128, true); B2_SET_SMEM(__nv_bfloat16, 0, true);
     B2_SET_SMEM(__nv_bfloat16, 128, false); B2_SET_SMEM(__nv_bfloat16, 0, false);
 #undef B2_SET_SMEM
-    B2_CUDA(cudaFuncSetAttribute(b16::gram_b16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmem));
-    B2_CUDA(cudaFuncSetAttribute(b16::gram_b16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmem));
+    B2_CUDA(cudaFuncSetAttribute(b16::sp::gram_b16_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::sp::kSmem));
+    B2_CUDA(cudaFuncSetAttribute(b16::gram_b16_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b16::kSmem));
     ctx->tc_attr_set = true;
   }
 
@@ -991,10 +992,10 @@ int launch_gram_tc(b2_ctx* ctx, const void* X, int x_dtype, const float* y, int6
   if (b16) {
     const int hm = mask != nullptr ? 1 + m_map_2d : 0;
     if (split)
-      b16::gram_b16_kernel<true><<<grid, kThreads, b16::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in, ctx->shift,
-                                                                              chunk_tiles, ctx->tc_part, ctx->tc_side);
+      b16::sp::gram_b16_split_kernel<<<grid, kThreads, b16::sp::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in,
+                                                                                      ctx->shift, chunk_tiles, ctx->tc_part, ctx->tc_side);
     else
-      b16::gram_b16_kernel<false><<<grid, kThreads, b16::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in, ctx->shift,
+      b16::gram_b16_single_kernel<<<grid, kThreads, b16::kSmem, ctx->stream>>>(tmX, tmY, tmM, y_map_2d, hm, keep, n, n_in, ctx->shift,
                                                                                chunk_tiles, ctx->tc_part, ctx->tc_side);
   } else if (x_dtype == B2_F32) {
     if (split) B2_LAUNCH_TC_D(float, true); else B2_LAUNCH_TC_D(float, false);

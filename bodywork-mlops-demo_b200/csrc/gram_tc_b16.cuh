@@ -1,48 +1,43 @@
-// gram_tc_b16.cuh -- the Gram kernel for bf16-STORED rows with D = 128 (BASELINE.json configs[1]: "10 M x 128 bf16-accum").
-// Included by gram_tc.cu inside its anonymous namespace (same PTX wrappers, same partial / finalize format).
+// gram_tc_b16.cuh -- Gram kernels for bf16-STORED rows with D = 128 (BASELINE.json configs[1]: "10 M x 128 bf16-accum").
+// Included by gram_tc.cu inside its anonymous namespace (same PTX wrappers, same partial / finalize format).  This file:
+// the shared device helpers and the SINGLE-OPERAND kernel (B2_PRECISION_BF16, the literal "bf16-accum" mode); the default
+// hi + lo mode is gram_tc_b16_split.cuh.
 //
-// Why a second kernel: at 260 B / row the generic kernel is bound by the shared-memory pipe, not by HBM
+// Why these kernels: at 260 B / row the generic kernel is bound by the shared-memory pipe, not by HBM
 // (profiles/r02_gram_tc_10Mx128_bf16_*: per 64-row tile 256 half-empty LDS.U16 wavefronts + 128 STS + 411 wavefronts of
-// MMA operand reads + 128 of TMA writes = 88 % of the pipe, and a quarter of all issued instructions were barrier
-// polls).  This kernel moves every byte through shared memory as few times as the data flow allows:
+// MMA operand reads + 128 of TMA writes = 88 % of the pipe).  Here every byte crosses shared memory as few times as the
+// data flow allows -- the B operand of the MMA is THE RAW TILE AS TMA DEPOSITED IT, never rewritten:
 //
 //   HBM --TMA, two [64 rows][64 features] boxes, SWIZZLE_128B--> raw tile (16 KB)                       128 wavefronts
-//     --ldmatrix.x4.trans: an 8 x 8 block comes back TRANSPOSED -- thread t holds feature f0 + t/4, rows 2(t%4), 2(t%4)+1
-//       as one packed bf16 pair: exactly the K-major operand word, no 2-byte loads (conflict-free through the swizzle) 128
-//     --hi = rn(x - c): ONE packed sub.rn.bf16x2 per pair;  split mode: 2 lo = rn(2 (x - hi) - 2c) in fp32
-//     --B = [hi | E] to smem (K-major canonical, the generic kernel's layout): one STS.32 per pair, a warp writes a whole
-//       128-byte core matrix                                                                              128 wavefronts
-//     --A = hi AND A = 2 lo to TENSOR MEMORY: tcgen05.st.16x128b.x2 takes the ldmatrix fragments as they are
-//       (register k of thread t -> lane t/4 (+8), column t%4 (+4)): no shuffles, and the MMAs read A without touching
-//       shared memory                                                                        MMA operand reads: 144 x 2
-//   The operand stage holds [E | hi | E] per 8-row K group (two copies of the 16 E columns around the 128 hi columns), the
-//   accumulator is 160 columns [Ea | G | Eb], and both MMAs of a K = 16 step have the SAME shape (M 128, N 144):
-//       [G | Eb] += hi^T     [hi | E]      B descriptor starts at hi, D at column 16
-//       [Ea | G] += (2 lo)^T [E | hi]      B descriptor starts at the first E copy, D at column 0
-//   so G = hi.hi + 2 lo.hi in ONE accumulator, Eb = hi^T E, Ea = 2 lo^T E.  One accumulator is enough because the fold
-//   symmetrises: 0.5 (G[a][b] + G[b][a]) = hi.hi + lo.hi + hi.lo, which is what tc_fold_value computes from the partials
-//   (this kernel writes [G | Eb] into the "A = hi" half of the partial, zeros and 0.5 Ea into the "A = lo" half).  Same
-//   flops as the generic kernel's two MMAs, and the 144 tensor-memory columns that a second full accumulator would take
-//   hold a three-deep ring of both A operands instead.  (A separate N = 16 MMA for lo^T E was measured first: it costs
-//   as much as a third of a full MMA -- the issue cost of an MMA does not shrink with N.)
-//   lo arithmetic: 2 lo = rn(2x - 2c - 2 hi) with two mixed-precision FMAs per element (fma.rn.f32.bf16: bf16 operands
-//   read straight out of the packed registers, fp32 accumulate, both exact here) -- no unpacking instructions.
+//     B = [x | E]: the raw tile read by the tensor core as an MN-major SWIZZLE_128B operand (three 64-column atoms:
+//         features 0..63, 64..127, and a third atom whose first 3 columns hold E = [1, y'_hi, y'_lo], written by the E
+//         warps with the same swizzle)                                                          MMA operand reads: 144
+//     A : ldmatrix.x4.trans of the same raw tile -- an 8 x 8 block comes back TRANSPOSED: thread t holds feature f0 + t/4,
+//         rows 2(t%4), 2(t%4)+1 as one packed bf16 pair (conflict-free through the swizzle)                           128
+//         hi = rn(x - c): ONE packed sub.rn.bf16x2 per pair
+//         --> TENSOR MEMORY: tcgen05.st.16x128b.x2 takes the ldmatrix fragments as they are (register k of thread t ->
+//         lane t/4 (+8), column t%4 (+4)): no shuffles, and no shared-memory stores at all in the transform
+//   tcgen05.mma per K = 16 step (M 128, N 144, A from tensor memory, B MN-major from shared memory):  D += hi^T [x | E]
+//   so D[i][j] = sum_r hi_i x_j with x the STORED value (exact in bf16).  The epilogue turns it into the centred product
+//   the fold expects,   sum_r hi_i v_j = D[i][j] - c_j * D[i][ones column]      (per-CTA partial, linear, fp64)
+//   and writes it into the "A = hi" half of the partial; the "A = lo" half is zero.  The fold symmetrises as always.
+//   One accumulator (x2 buffers) = 288 tensor-memory columns; 128 more hold a 4-deep ring of A operands.
+//   (With hi + lo operands the same scheme gives 0.61 of the roofline but every accumulator entry then carries
+//   c_j * sum_r v_i, whose fp32 truncation costs a factor 3 in coefficient accuracy -- hence the separate split kernel.)
+//   Measured on the way here (profiles/r02_b16_ablations.txt): a third N = 16 MMA per K step costs 58 cycles (an MMA
+//   costs max(58, N / 2) cycles whatever its N: tools/ubench_umma.cu); unpacking bf16 pairs with shifts and masks made
+//   the lo arithmetic 150 instructions per warp and tile; MMAs issued under `lane == 0` are wrapped in waterfall loops.
 #pragma once
 
 namespace b16 {
 
-constexpr int kRaw = 6;                                   // raw tile stages (16 KB each)
-constexpr int kOpsMax = 4;                                // operand stages (smem B ring + tensor-memory A rings): 3 with two A
-                                                          // operands (192 tensor-memory columns), 4 in single-operand mode
-constexpr uint32_t kRawBytes = kTcRows * 128 * 2;         // 16384
-constexpr uint32_t kRawHalf = kTcRows * 128;              // 8192: one [64][64] bf16 box
-constexpr uint32_t kLBO = (2 + 16 + 2) * kOpSBO;          // 2560: E | hi | E groups per 8-row K group
-constexpr uint32_t kHiOff = 2 * kOpSBO;                   // hi groups inside a K group
-constexpr uint32_t kE1Off = (2 + 16) * kOpSBO;            // the E copy behind hi (B = [hi | E])
-constexpr uint32_t kOpBytes = kKGroups * kLBO;            // 20480
+constexpr int kRaw = 6;                                   // raw tile stages
+constexpr int kOpsMax = 4;                                // tensor-memory A-operand stages
+constexpr uint32_t kRawHalf = kTcRows * 128;              // 8192: one [64 rows][64 columns] bf16 atom
+constexpr uint32_t kRawX = 2 * kRawHalf;                  // 16384: the two feature atoms TMA fills
+constexpr uint32_t kRawBytes = 3 * kRawHalf;              // 24576: + the E atom
 constexpr uint32_t kOffRaw = 0;
-constexpr uint32_t kOffOp = kOffRaw + kRaw * kRawBytes;   // 98304
-constexpr uint32_t kOffY = kOffOp + kOpsMax * kOpBytes;   // 180224
+constexpr uint32_t kOffY = kOffRaw + kRaw * kRawBytes;    // 147456
 constexpr uint32_t kYBytes = kTcRows * 4;                 // 256
 constexpr uint32_t kMBytes = 128;                         // 64 mask bytes, padded (TMA destinations are 128-byte aligned)
 constexpr uint32_t kOffMask = kOffY + kRaw * kYBytes;
@@ -52,14 +47,19 @@ constexpr uint32_t kOffTmemPtr = kOffBar + kBars * 8;
 constexpr uint32_t kOffShift = kOffTmemPtr + 16;
 constexpr uint32_t kSmem = kOffShift + (kMaxD + 4) * 4 + 1024;
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
-// tensor memory: accumulator [Ea 16 | G 128 | Eb 16] double buffered at 0 / 160, A = hi ring at 320 + 32 s, A = 2 lo ring
-// at 416 + 32 s
-constexpr uint32_t kAccStride = 160;
-constexpr uint32_t kTmemAHi = 320;
-constexpr uint32_t kTmemALo = 416;
+// tensor memory: accumulator [G 128 | E 16] double buffered at 0 / 144, A = hi ring at 288 + 32 s
+constexpr uint32_t kAccStride = 144;
+constexpr uint32_t kTmemAHi = 288;
 
+// MN-major SWIZZLE_128B operand (cute::UMMA::SmemDescriptor, version 1): 64-column atoms `kRawHalf` bytes apart (leading
+// byte offset), 8-row K groups 1024 bytes apart (stride byte offset), layout type 2
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(kRawHalf >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = f32, A = B = bf16, A K-major (tensor memory), B MN-major (bit 16), N, M = 128
 __host__ __device__ constexpr uint32_t idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
@@ -108,9 +108,8 @@ __device__ __forceinline__ float fma_bf16_hi(uint32_t a2, uint32_t b2, float c) 
       : "=f"(d) : "r"(a2), "r"(b2), "f"(c));
   return d;
 }
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-               ::"r"(taddr), "r"(0u) : "memory");
+__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -138,23 +137,22 @@ __device__ __forceinline__ void wait_lean(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
-gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep, int64_t n_rows,
                 int64_t n_shift, const float* __restrict__ shift, int chunk_tiles, double* __restrict__ part,
                 double* __restrict__ side) {
-  constexpr int kOps = SPLIT ? 3 : kOpsMax;
+  constexpr int kOps = kOpsMax;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const uint32_t bar_raw_full = sbase + kOffBar;                 // [kRaw]
-  const uint32_t bar_raw_empty = bar_raw_full + 8 * kRaw;        // [kRaw]
-  const uint32_t bar_op_full = bar_raw_empty + 8 * kRaw;         // [kOps]
-  const uint32_t bar_op_empty = bar_op_full + 8 * kOpsMax;       // [kOps]
+  const uint32_t bar_raw_full = sbase + kOffBar;                 // [kRaw]  TMA bytes landed
+  const uint32_t bar_raw_empty = bar_raw_full + 8 * kRaw;        // [kRaw]  the MMAs that read the stage as B have retired
+  const uint32_t bar_op_full = bar_raw_empty + 8 * kRaw;         // [kOps]  A operands in tensor memory + E columns written
+  const uint32_t bar_op_empty = bar_op_full + 8 * kOpsMax;       // [kOps]  the MMAs that read the A stage have retired
   const uint32_t bar_acc_full = bar_op_empty + 8 * kOpsMax;      // [2]
   const uint32_t bar_acc_empty = bar_acc_full + 16;              // [2]
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
@@ -169,7 +167,7 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRaw; ++s) {
       mbar_init(bar_raw_full + 8 * s, 1);
-      mbar_init(bar_raw_empty + 8 * s, kProducers);
+      mbar_init(bar_raw_empty + 8 * s, 1);
     }
     for (int s = 0; s < kOps; ++s) {
       mbar_init(bar_op_full + 8 * s, kProducers);
@@ -190,27 +188,20 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + kOffTmemPtr) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // the unused E rows of the operand stages read as 0
-  for (uint32_t o = threadIdx.x * 16; o < kOpsMax * kOpBytes; o += kThreads * 16)
-    *reinterpret_cast<uint4*>(smem + kOffOp + o) = make_uint4(0, 0, 0, 0);
+  // the E atoms: only 3 of their 64 columns are ever written; the MMA reads the first 16
+  for (int st = 0; st < kRaw; ++st)
+    for (uint32_t o = threadIdx.x * 16; o < kRawHalf; o += kThreads * 16)
+      *reinterpret_cast<uint4*>(smem + kOffRaw + st * kRawBytes + kRawX + o) = make_uint4(0, 0, 0, 0);
   for (int j = threadIdx.x; j <= kMaxD; j += kThreads) shift_s[j] = shift_value(shift, j, n_shift);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (SPLIT && warp >= 4 && warp < 8) {     // Ea is only ever accumulated into (the first MMA of a chunk initialises [G | Eb])
-    tmem_st16_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16));
-    tmem_st16_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccStride);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
 
   if (warp == 0) {
     // ===== TMA producer (the whole warp runs the loop, one elected lane issues) =====
-    const uint32_t tx = kRawBytes + kTcRows * 4 + (has_mask ? kTcRows : 0);
+    const uint32_t tx = kRawX + kTcRows * 4 + (has_mask ? kTcRows : 0);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -231,70 +222,61 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer (the whole warp runs the loop, one elected lane issues) =====
-    int os = 0;
+    int os = 0, rs = 0;
     uint32_t oph = 0;
     int in_chunk = 0, chunk = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int b = chunk & 1;
       if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-      wait_lean(bar_op_full + 8 * os, oph);
+      wait_lean(bar_op_full + 8 * os, oph);       // implies raw_full of this tile (the producers waited for it)
       tc_fence_after();
       const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
       if (elect_one()) {
-        const uint32_t op_addr = sbase + kOffOp + os * kOpBytes;
         const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
-        // descriptors of consecutive K steps differ by a constant in the address field (no carry: smem addresses < 2^18)
-        const uint64_t desc_e = make_smem_desc(op_addr, kLBO), desc_hi = make_smem_desc(op_addr + kHiOff, kLBO);
+        // K steps of 16 rows are 2048 bytes apart inside the atoms (no carry into the other descriptor fields)
+        const uint64_t desc0 = make_desc_mn128(sbase + kOffRaw + rs * kRawBytes);
 #pragma unroll
         for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint64_t step = (uint64_t)((k2 * 2 * kLBO) >> 4);
-          umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi + step, idesc(144),
-                  (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                             // [G | Eb] += hi^T [hi | E]
-          if constexpr (SPLIT)
-            umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e + step, idesc(144), 1u);
-                                                                                                    // [Ea | G] += 2 lo^T [E | hi]
+          const uint64_t b_desc = desc0 + (uint64_t)((k2 * 2048) >> 4);
+          umma_ts(tmem_acc, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), b_desc, idesc(144),
+                  (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                              // D += hi^T [x | E]
         }
         umma_commit(bar_op_empty + 8 * os);
+        umma_commit(bar_raw_empty + 8 * rs);
         if (last) umma_commit(bar_acc_full + 8 * b);
       }
       __syncwarp();
       if (last) { in_chunk = 0; ++chunk; }
       else ++in_chunk;
       if (++os == kOps) { os = 0; oph ^= 1; }
+      if (++rs == kRaw) rs = 0;
     }
   } else if (warp == 2 || warp == 3) {
-    // ===== E warps: operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' (one row per lane) =====
+    // ===== E warps: B columns 128..130 = [1, y'_hi, y'_lo] in the third atom of the raw stage (row r: 128-byte rows, the
+    // 16-byte chunk index XORed with r % 8 like the TMA swizzle), and the CUDA-core sums of y' (one row per lane) =====
     const float c_y = shift_s[kMaxD];
     double sy = 0.0, syy = 0.0, cnt = 0.0;
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     const int rr = lane + 32 * (warp - 2);
+    const uint32_t e_off = kRawX + (uint32_t)rr * 128u + ((uint32_t)(rr & 7) << 4);
     for (int it = 0; it < my_tiles; ++it) {
       wait_lean(bar_raw_full + 8 * rs, rph);
       wait_lean(bar_op_empty + 8 * os, oph ^ 1);
-      tc_fence_after();
       const int64_t left = n_rows - (tile_begin + it) * kTcRows;
       bool use = rr < left;
       if (use && has_mask) use = (ld_shared_u8(sbase + kOffMask + rs * kMBytes + rr) == (uint32_t)keep);
       const float yv = use ? ld_shared_f32(sbase + kOffY + rs * kYBytes + rr * 4) - c_y : 0.f;
       uint32_t yh, yl;
       split2(yv, 0.f, yh, yl);
-      const uint32_t dst = sbase + kOffOp + os * kOpBytes + (rr >> 3) * kLBO + (rr & 7) * 2;
-      st_shared_u16(dst + kE1Off, use ? 0x3F80u : 0u);
-      st_shared_u16(dst + kE1Off + 16, yh);
-      st_shared_u16(dst + kE1Off + 32, yl);
-      if constexpr (SPLIT) {                  // the copy in front of hi: B = [E | hi] of the A = 2 lo MMA
-        st_shared_u16(dst, use ? 0x3F80u : 0u);
-        st_shared_u16(dst + 16, yh);
-        st_shared_u16(dst + 32, yl);
-      }
+      const uint32_t dst = sbase + kOffRaw + rs * kRawBytes + e_off;
+      st_shared_u16(dst, use ? 0x3F80u : 0u);
+      st_shared_u16(dst + 2, yh);
+      st_shared_u16(dst + 4, yl);
       sy += (double)yv; syy += (double)(yv * yv); cnt += use ? 1.0 : 0.0;
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_op_full + 8 * os);
-        mbar_arrive(bar_raw_empty + 8 * rs);
-      }
+      if (lane == 0) mbar_arrive(bar_op_full + 8 * os);
       if (++rs == kRaw) { rs = 0; rph ^= 1; }
       if (++os == kOps) { os = 0; oph ^= 1; }
     }
@@ -309,7 +291,7 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       ys[0] = sy; ys[1] = syy; ys[2] = cnt;
     }
   } else if (warp < 8) {
-    // ===== epilogue: TMEM -> fp64 partial in global (column-major [col][feature]) =====
+    // ===== epilogue: TMEM -> fp64 partial in global (column-major [col][feature]); lane = feature i =====
     const int w = warp & 3;
     double* my_part = part + (size_t)blockIdx.x * kTcAccElems + w * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(w * 32) << 16);
@@ -317,34 +299,45 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int b = chunk & 1;
       wait_lean(bar_acc_full + 8 * b, (chunk >> 1) & 1);
       tc_fence_after();
-      // accumulator columns [Ea | G | Eb] -> partial columns: G, Eb -> [0, 144) (the "A = hi" half), 0.5 Ea -> the E
-      // columns of the "A = lo" half
+      // E block first: column 128 = sum_r v_i (the ones column), 129 / 130 = sum_r v_i y'
+      uint32_t re[16];
+      tmem_ld16(lane_base + (uint32_t)b * kAccStride + 128u, re);
+      tmem_ld_wait();
+      const double s1 = (double)__uint_as_float(re[0]);
+      {
+        double* dst = my_part + (size_t)128 * kTcM;
+        if (chunk == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = (double)__uint_as_float(re[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] += (double)__uint_as_float(re[j]);
+        }
+      }
+      // G: D[i][j] = sum_r v_i x_j  ->  sum_r v_i v_j = D[i][j] - c_j sum_r v_i   (x_j = v_j + c_j exactly on the B side)
 #pragma unroll 1
-      for (int p = SPLIT ? 0 : 1; p < (int)kAccStride / 16; ++p) {
+      for (int p = 0; p < 8; ++p) {
         uint32_t r[16];
         tmem_ld16(lane_base + (uint32_t)b * kAccStride + (uint32_t)(p * 16), r);
         tmem_ld_wait();
-        double* dst = my_part + (size_t)(p == 0 ? kTcN + 128 : (p - 1) * 16) * kTcM;
-        const double scale = p == 0 ? 0.5 : 1.0;
+        double* dst = my_part + (size_t)(p * 16) * kTcM;
         if (chunk == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = scale * (double)__uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j)
+            dst[(size_t)j * kTcM] = fma(-(double)shift_s[p * 16 + j], s1, (double)__uint_as_float(r[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] += scale * (double)__uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j)
+            dst[(size_t)j * kTcM] += fma(-(double)shift_s[p * 16 + j], s1, (double)__uint_as_float(r[j]));
         }
-      }
-      if constexpr (SPLIT) {                  // Ea starts the next chunk of this buffer from zero
-        tmem_st16_zero(lane_base + (uint32_t)b * kAccStride);
-        tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * b);
     }
-    // the rest of the "A = lo" half: lo.hi is already inside G (twice: the fold halves the symmetrised sum)
+    // the "A = lo" half of the partial format stays empty: both operand halves went into the one accumulator
 #pragma unroll 1
-    for (int p = 0; p < kTcN / 16 - (SPLIT ? 1 : 0); ++p) {
+    for (int p = 0; p < kTcN / 16; ++p) {
       double* dst = my_part + (size_t)(kTcN + p * 16) * kTcM;
 #pragma unroll
       for (int j = 0; j < 16; ++j) dst[(size_t)j * kTcM] = 0.0;
@@ -355,20 +348,16 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int q = t & 3, s = t >> 2;
     const int j4 = lane & 3, f8 = lane >> 2;
     // ldmatrix row address of lane L: matrix b = L / 8 (features 32q + 8b ..), row L % 8 of the 8-row group; the 16-byte
-    // chunk index is XORed with the row (SWIZZLE_128B; the rows of a box are 128 bytes apart)
+    // chunk index is XORed with the row (SWIZZLE_128B; the rows of an atom are 128 bytes apart)
     const uint32_t lm_off = (uint32_t)(q >> 1) * kRawHalf + (uint32_t)(lane & 7) * 128u +
                             ((uint32_t)((4 * (q & 1) + (lane >> 3)) ^ (lane & 7)) << 4);
     uint32_t cc[4];      // (c, c) as packed bf16 of this thread's four features 32q + 8b + lane/4
-    float m2c[4];        // -2 c
-    constexpr uint32_t kTwo = 0x40004000u, kMinusTwo = 0xC000C000u;      // bf16 pairs (2, 2) and (-2, -2)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const float c = shift_s[32 * q + 8 * b + f8];
       const __nv_bfloat162 cp = __floats2bfloat162_rn(c, c);     // exact: c is bf16-representable
       cc[b] = *reinterpret_cast<const uint32_t*>(&cp);
-      m2c[b] = -2.f * c;
     }
-    const uint32_t st_off = (uint32_t)(2 * s) * kLBO + kHiOff + (uint32_t)(4 * q) * kOpSBO + (uint32_t)lane * 4u;
     const uint32_t tm_lane = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(8 * s);
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
@@ -376,32 +365,24 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       wait_lean(bar_raw_full + 8 * rs, rph);
       wait_lean(bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
-      const uint32_t raw_addr = sbase + kOffRaw + rs * kRawBytes + lm_off + (uint32_t)(2 * s) * 1024u;
+      const uint32_t stage = sbase + kOffRaw + rs * kRawBytes;
+      const uint32_t raw_addr = stage + lm_off + (uint32_t)(2 * s) * 1024u;
       uint32_t R[2][4];
       ldsm_x4_trans(raw_addr, R[0]);
       ldsm_x4_trans(raw_addr + 1024u, R[1]);
       const int64_t left = n_rows - (tile_begin + it) * kTcRows;
-      uint32_t H[2][4], L[2][4];
+      uint32_t H[2][4];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t raw = R[g][b];
-          const uint32_t hp = sub_bf16x2(raw, cc[b]);                  // hi = rn(x - c), both rows of the pair
-          H[g][b] = hp;
-          if constexpr (SPLIT) {
-            // 2 lo = rn(2x - 2c - 2 hi): both FMAs are exact in fp32 (lo has at most 16 significant bits)
-            const float l0 = fma_bf16_lo(hp, kMinusTwo, fma_bf16_lo(raw, kTwo, m2c[b]));
-            const float l1 = fma_bf16_hi(hp, kMinusTwo, fma_bf16_hi(raw, kTwo, m2c[b]));
-            const __nv_bfloat162 lp = __floats2bfloat162_rn(l0, l1);
-            L[g][b] = *reinterpret_cast<const uint32_t*>(&lp);
-          }
-        }
+        for (int b = 0; b < 4; ++b) H[g][b] = sub_bf16x2(R[g][b], cc[b]);      // hi = rn(x - c), both rows of the pair
       }
-      if (has_mask || left < kTcRows) {          // rows 16s + 8g + 2 j4 (low half of the pair) and + 1 (high half)
+      const bool masked = has_mask || left < kTcRows;
+      if (masked) {
         const uint32_t m_addr = sbase + kOffMask + rs * kMBytes;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
+          // A side: rows 16s + 8g + 2 j4 (low half of the pair) and + 1 (high half) of this thread's fragments
           const int r0 = 16 * s + 8 * g + 2 * j4;
           bool u0 = r0 < left, u1 = (r0 + 1) < left;
           if (has_mask) {
@@ -410,33 +391,25 @@ gram_b16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           const uint32_t keep32 = (u0 ? 0x0000ffffu : 0u) | (u1 ? 0xffff0000u : 0u);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            H[g][b] &= keep32;
-            if constexpr (SPLIT) L[g][b] &= keep32;
-          }
+          for (int b = 0; b < 4; ++b) H[g][b] &= keep32;
+          // B side: a dropped row multiplies A = 0, but 0 * (NaN or Inf) would still poison the sums, so the warp also
+          // clears its 64-byte segment of every dropped row of the raw tile (row 16s + 8g + lane / 4, chunk lane % 4)
+          const int rz = 16 * s + 8 * g + f8;
+          bool uz = rz < left;
+          if (uz && has_mask) uz = (ld_shared_u8(m_addr + rz) == (uint32_t)keep);
+          if (!uz)
+            st_shared_zero16(stage + (uint32_t)(q >> 1) * kRawHalf + (uint32_t)rz * 128u +
+                             ((uint32_t)((4 * (q & 1) + j4) ^ (rz & 7)) << 4));
         }
-      }
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          st_shared_b32(sbase + kOffOp + os * kOpBytes + st_off + (uint32_t)g * kLBO + (uint32_t)b * kOpSBO, H[g][b]);
       }
       const uint32_t ta = tm_lane + (uint32_t)(os * 32);
       tmem_st_16x128b_x2(ta + kTmemAHi, H[0][0], H[0][1], H[1][0], H[1][1]);
       tmem_st_16x128b_x2(ta + kTmemAHi + (16u << 16), H[0][2], H[0][3], H[1][2], H[1][3]);
-      if constexpr (SPLIT) {
-        tmem_st_16x128b_x2(ta + kTmemALo, L[0][0], L[0][1], L[1][0], L[1][1]);
-        tmem_st_16x128b_x2(ta + kTmemALo + (16u << 16), L[0][2], L[0][3], L[1][2], L[1][3]);
-      }
       tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
+      if (masked) fence_proxy_async_smem();      // the cleared rows (generic proxy) -> the MMA's operand reads (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_op_full + 8 * os);
-        mbar_arrive(bar_raw_empty + 8 * rs);
-      }
+      if (lane == 0) mbar_arrive(bar_op_full + 8 * os);
       if (++rs == kRaw) { rs = 0; rph ^= 1; }
       if (++os == kOps) { os = 0; oph ^= 1; }
     }

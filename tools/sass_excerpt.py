@@ -9,7 +9,7 @@ for m in ("UTCHMMA", "UTMALDG", "UBLKCP", "LDTM", "STTM", "LDSM", "FHFMA.BF16", 
     print(f"{m:34s} {sass.count(m)}")
 funcs = re.split(r"(?=\s+Function : )", sass)
 WANT = r"LDSM|FHFMA|HFMA2\.BF16|HADD2\.BF16|ELECT|UTCHMMA|UTMALDG|UBLKCP|LDTM|STTM|UTCBAR|SYNCS\.|DMMA|MUFU\.RCP64H|FFMA2|\.SYS|MEMBAR|ATOMG|REDG|NANOSLEEP|UTCATOM|DFMA|LDS\.128|STS\.128|BAR\.SYNC|ST\.E|LDG"
-for pat in ("gram_tc_kernelIfLi128ELb1", "gram_b16_kernelILb1", "gram_b16_kernelILb0", "tc_shift_kernelIf", "tc_finalize_kernel", "solve_cholesky_kernel", "solve_eigvals_kernel",
+for pat in ("gram_tc_kernelIfLi128ELb1", "gram_b16_split_kernel", "gram_b16_single_kernel", "tc_shift_kernelIf", "tc_finalize_kernel", "solve_cholesky_kernel", "solve_eigvals_kernel",
             "score_narrow_kernelIfLi1ELb1ELb1", "gram_narrow_kernelIfLi8", "p2p_scatter_kernel", "p2p_gather_kernel"):
     body = next((f for f in funcs if re.search(r"Function : \S*" + pat, f)), None)
     if body is None:
