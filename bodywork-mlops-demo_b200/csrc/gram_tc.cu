@@ -201,7 +201,8 @@ tc_shift_kernel(const T* __restrict__ X, const float* __restrict__ y, int64_t n,
 #pragma unroll 8
     for (int64_t s = s0 + g; s < s1; s += kShiftGroups) {
       const int64_t row = s * stride;
-      acc += (j < d) ? raw_ld_global<T>(X + row * ldx + j) : __ldg(y + row);
+      const float v = (j < d) ? raw_ld_global<T>(X + row * ldx + j) : __ldg(y + row);
+      acc += (fabsf(v) <= 3.0e38f) ? v : 0.f;     // the sample ignores the row mask: a dropped row may hold NaN / Inf
     }
   }
   sub[g][j] = acc;

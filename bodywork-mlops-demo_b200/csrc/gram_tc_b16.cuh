@@ -379,6 +379,7 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
       const bool masked = has_mask || left < kTcRows;
       if (masked) {
+        __syncwarp();                            // the ldmatrix reads above vs the clearing stores below (other lanes' rows)
         const uint32_t m_addr = sbase + kOffMask + rs * kMBytes;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {

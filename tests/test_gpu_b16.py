@@ -1,5 +1,6 @@
-"""The bf16-storage D = 128 Gram kernel (csrc/gram_tc_b16.cuh: swizzled TMA boxes -> ldmatrix.trans -> both A operands in
-tensor memory, one symmetrised accumulator) against the fp64 oracle of the SAME bf16-rounded rows.
+"""The bf16-storage D = 128 Gram kernels (csrc/gram_tc_b16_split.cuh: hi + lo operands, swizzled TMA boxes -> ldmatrix.trans
+-> both A operands in tensor memory, one symmetrised accumulator; csrc/gram_tc_b16.cuh: single operand, the raw TMA tile
+is the MMA's B operand) against the fp64 oracle of the SAME bf16-rounded rows.
 
 Tolerances: the statistic within 2e-6 relative, the row count exact, coefficients within 2e-5 (contract 1e-4) in the
 default hi+lo mode; the single-operand mode ('bf16-accum') within the 1e-4 contract at large n only (its operand
@@ -82,6 +83,27 @@ def test_b16_mask_equals_gather_and_row_pitch(ctx, n, keep, ldx):
     ctx.gram_import(S)
     coef, _ = ctx.solve()
     assert np.max(np.abs(coef - orc.fit_from_stats(So)["coef"])) < COEF_TOL
+
+
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_b16_dropped_rows_may_hold_nan(ctx, precision):
+    """A masked-out row never reaches the statistic, whatever it holds: the single-operand kernel feeds the RAW tile to the
+    tensor core as the B operand, so it clears dropped rows in shared memory first (0 * NaN would poison the sums)."""
+    n = 50_001
+    bits, Xr, y = _rows(n, seed=17)
+    mask = (np.random.RandomState(3).rand(n) < 0.7).astype(np.uint8)
+    bits = bits.copy(); y = y.copy()
+    drop = np.flatnonzero(mask == 0)
+    bits[drop[::3]] = 0x7FC0            # NaN rows
+    bits[drop[1::3]] = 0x7F80           # +Inf rows
+    y[drop[::5]] = np.nan
+    prec = b2.PRECISION_SPLIT if precision == "split" else b2.PRECISION_BF16
+    S = _accumulate(ctx, bits, y, mask=mask, keep=1, precision=prec)
+    assert np.all(np.isfinite(S))
+    sel = mask == 1
+    So = orc.gram_stats(Xr[sel], y[sel])
+    assert S[128, 128] == int(sel.sum())
+    assert _rel(S, So) < (2e-6 if precision == "split" else 2e-4)
 
 
 def test_b16_is_deterministic_and_additive(ctx):
