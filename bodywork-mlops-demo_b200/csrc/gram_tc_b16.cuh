@@ -221,36 +221,41 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       if (++s == kRaw) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (the whole warp runs the loop, one elected lane issues) =====
-    int os = 0, rs = 0;
-    uint32_t oph = 0;
-    int in_chunk = 0, chunk = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = chunk & 1;
-      if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-      wait_lean(bar_op_full + 8 * os, oph);       // implies raw_full of this tile (the producers waited for it)
-      tc_fence_after();
-      const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
-      if (elect_one()) {
-        const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
-        // K steps of 16 rows are 2048 bytes apart inside the atoms (no carry into the other descriptor fields)
-        const uint64_t desc0 = make_desc_mn128(sbase + kOffRaw + rs * kRawBytes);
+    // ===== MMA issuer: ONE elected thread runs the whole loop, unrolled over the raw stages so that every descriptor,
+    // tensor-memory address and barrier address is a constant offset from a loop-invariant uniform register: the path
+    // from "last MMA of tile t issued" to "first MMA of tile t+1 issued" must be shorter than the tensor core's queue =====
+    static_assert(kRaw % kOps == 0 || kOps == 4, "stage bookkeeping below assumes kOps = 4");
+    if (elect_one()) {
+      uint32_t oph = 0;
+      int in_chunk = 0, chunk = 0, it = 0, os = 0;
+      const uint64_t desc00 = make_desc_mn128(sbase + kOffRaw);
+      while (it < my_tiles) {
 #pragma unroll
-        for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint64_t b_desc = desc0 + (uint64_t)((k2 * 2048) >> 4);
-          umma_ts(tmem_acc, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), b_desc, idesc(144),
-                  (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                              // D += hi^T [x | E]
+        for (int rs = 0; rs < kRaw; ++rs) {
+          if (it < my_tiles) {
+            const int b = chunk & 1;
+            if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
+            wait_lean(bar_op_full + 8 * os, oph);     // implies raw_full of this tile (the producers waited for it)
+            tc_fence_after();
+            const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
+            const uint32_t a_hi = tmem_base + kTmemAHi + (uint32_t)(os * 32);
+            // K steps of 16 rows are 2048 bytes apart inside the atoms, stages kRawBytes (no carry into other fields)
+#pragma unroll
+            for (int k2 = 0; k2 < kTcRows / 16; ++k2)
+              umma_ts(tmem_acc, a_hi + (uint32_t)(k2 * 8), desc00 + (uint64_t)((rs * kRawBytes + k2 * 2048) >> 4), idesc(144),
+                      (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                          // D += hi^T [x | E]
+            umma_commit(bar_op_empty + 8 * os);
+            umma_commit(bar_raw_empty + 8 * rs);
+            if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
+            else ++in_chunk;
+            ++it;
+            if (++os == kOps) { os = 0; oph ^= 1; }
+          }
         }
-        umma_commit(bar_op_empty + 8 * os);
-        umma_commit(bar_raw_empty + 8 * rs);
-        if (last) umma_commit(bar_acc_full + 8 * b);
       }
-      __syncwarp();
-      if (last) { in_chunk = 0; ++chunk; }
-      else ++in_chunk;
-      if (++os == kOps) { os = 0; oph ^= 1; }
-      if (++rs == kRaw) rs = 0;
     }
+    __syncwarp();
   } else if (warp == 2 || warp == 3) {
     // ===== E warps: B columns 128..130 = [1, y'_hi, y'_lo] in the third atom of the raw stage (row r: 128-byte rows, the
     // 16-byte chunk index XORed with r % 8 like the TMA swizzle), and the CUDA-core sums of y' (one row per lane) =====

@@ -147,37 +147,42 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == kRaw) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (the whole warp runs the loop, one elected lane issues) =====
-    int os = 0;
-    uint32_t oph = 0;
-    int in_chunk = 0, chunk = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int b = chunk & 1;
-      if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-      wait_lean(bar_op_full + 8 * os, oph);
-      tc_fence_after();
-      const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
-      if (elect_one()) {
-        const uint32_t op_addr = sbase + kOffOp + os * kOpBytes;
-        const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
-        // descriptors of consecutive K steps differ by a constant in the address field (no carry: smem addresses < 2^18)
-        const uint64_t desc_e = make_smem_desc(op_addr, kLBO), desc_hi = make_smem_desc(op_addr + kHiOff, kLBO);
+    // ===== MMA issuer: ONE elected thread runs the whole loop, unrolled over the operand stages so that every descriptor,
+    // tensor-memory address and barrier address is a constant offset from a loop-invariant uniform register: the path
+    // from "last MMA of tile t issued" to "first MMA of tile t+1 issued" must be shorter than the tensor core's queue =====
+    if (elect_one()) {
+      uint32_t oph = 0;
+      int in_chunk = 0, chunk = 0, it = 0;
+      const uint64_t desc_e0 = make_smem_desc(sbase + kOffOp, kLBO), desc_hi0 = make_smem_desc(sbase + kOffOp + kHiOff, kLBO);
+      while (it < my_tiles) {
 #pragma unroll
-        for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-          const uint64_t step = (uint64_t)((k2 * 2 * kLBO) >> 4);
-          umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi + step, idesc_k(144),
-                  (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                             // [G | Eb] += hi^T [hi | E]
-          umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e + step, idesc_k(144), 1u);
+        for (int os = 0; os < kOps; ++os) {
+          if (it < my_tiles) {
+            const int b = chunk & 1;
+            if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
+            wait_lean(bar_op_full + 8 * os, oph);
+            tc_fence_after();
+            const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
+            // descriptors of other stages / K steps differ by a constant in the address field (no carry: addresses < 2^18)
+#pragma unroll
+            for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
+              const uint64_t step = (uint64_t)((os * kOpBytes + k2 * 2 * kLBO) >> 4);
+              umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi0 + step, idesc_k(144),
+                      (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                         // [G | Eb] += hi^T [hi | E]
+              umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e0 + step, idesc_k(144), 1u);
                                                                                                     // [Ea | G] += 2 lo^T [E | hi]
+            }
+            umma_commit(bar_op_empty + 8 * os);
+            if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
+            else ++in_chunk;
+            ++it;
+          }
         }
-        umma_commit(bar_op_empty + 8 * os);
-        if (last) umma_commit(bar_acc_full + 8 * b);
+        oph ^= 1;
       }
-      __syncwarp();
-      if (last) { in_chunk = 0; ++chunk; }
-      else ++in_chunk;
-      if (++os == kOps) { os = 0; oph ^= 1; }
     }
+    __syncwarp();
   } else if (warp == 2 || warp == 3) {
     // ===== E warps: operand columns [1, y'_hi, y'_lo] and the CUDA-core sums of y' (one row per lane) =====
     const float c_y = shift_s[kMaxD];

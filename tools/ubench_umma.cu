@@ -28,15 +28,17 @@ __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint3
 }
 
 // mode bit 0: A from smem (else TMEM); bit 1: alternate two accumulators; bit 2: rotate the B stage (3 stages)
-__global__ void __launch_bounds__(128, 1) k(int n_cols, int mode, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int n_cols, int mode, int reps, long long* out, int commit_every) {
   extern __shared__ uint8_t raw[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_ptr;
   const uint32_t sbase = (smem_u32(raw) + 1023u) & ~1023u;
   for (uint32_t o = threadIdx.x * 16; o < 3 * 40960; o += blockDim.x * 16)
     *reinterpret_cast<uint4*>(raw + (sbase - smem_u32(raw)) + o) = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(128, 1) k(int n_cols, int mode, int reps, long
             if (mode & 1) mma_ss(d, make_desc(sbase + st + k2 * 2 * lbo + 20480u, lbo), b, id, 1u);
             else mma_ts(d, tb + 480 + k2 * 8, b, id, 1u);
           }
+          if (commit_every > 0 && (r % commit_every) == commit_every - 1)     // a pipeline stage hand-off, nobody waits on it
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
       }
@@ -96,7 +100,7 @@ int main() {
       printf("grid %3d  A %-4s  acc %s  B %-6s :", grid, (mode & 1) ? "smem" : "tmem", (mode & 2) ? "2" : "1", (mode & 4) ? "rotate" : "same");
       for (int n : ns) {
         if ((mode & 2) && n > 240) { printf("  N%-3d    -", n); continue; }
-        k<<<grid, 128, smem>>>(n, mode, reps, out);
+        k<<<grid, 128, smem>>>(n, mode, reps, out, 0);
         long long h[148];
         cudaError_t e = cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf(" CUDA error %s\n", cudaGetErrorString(e)); return 1; }
@@ -106,6 +110,19 @@ int main() {
       }
       printf("\n");
     }
+  }
+  // tcgen05.commit between groups of MMAs (as a pipelined kernel issues them: one or two per tile of 4 or 8 MMAs)
+  for (int ce : {0, 4, 2, 1}) {
+    printf("grid 148  A tmem  N144  commit every %d MMAs :", ce * 4);
+    for (int mode : {0, 1}) {
+      k<<<148, 128, smem>>>(144, mode, reps, out, ce);
+      long long h[148];
+      cudaMemcpy(h, out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("  %s %5.1f cycles / MMA", mode ? "A smem" : "A tmem", (double)mx / (reps * 4));
+    }
+    printf("\n");
   }
   return 0;
 }
