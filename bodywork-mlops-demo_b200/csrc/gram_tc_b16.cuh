@@ -79,6 +79,17 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// the same with the descriptor as (runtime low word, compile-time high word): one register per MMA instead of two
+template <uint32_t DESC_HI>
+__device__ __forceinline__ void umma_ts32(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t id, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 d, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(bdesc_lo), "r"(id), "r"(accumulate), "n"(DESC_HI)
+      : "memory");
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -228,7 +239,8 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (elect_one()) {
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0, it = 0, os = 0;
-      const uint64_t desc00 = make_desc_mn128(sbase + kOffRaw);
+      const uint32_t desc00 = (uint32_t)make_desc_mn128(sbase + kOffRaw);      // low word; the high word is a constant
+      constexpr uint32_t kDescHi = (uint32_t)((((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61)) >> 32);
       while (it < my_tiles) {
 #pragma unroll
         for (int rs = 0; rs < kRaw; ++rs) {
@@ -243,7 +255,7 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             // K steps of 16 rows are 2048 bytes apart inside the atoms, stages kRawBytes (no carry into other fields)
 #pragma unroll
             for (int k2 = 0; k2 < kTcRows / 16; ++k2)
-              umma_ts(tmem_acc, a_hi + (uint32_t)(k2 * 8), desc00 + (uint64_t)((rs * kRawBytes + k2 * 2048) >> 4), idesc(144),
+              umma_ts32<kDescHi>(tmem_acc, a_hi + (uint32_t)(k2 * 8), desc00 + (uint32_t)((rs * kRawBytes + k2 * 2048) >> 4), idesc(144),
                       (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                          // D += hi^T [x | E]
             umma_commit(bar_op_empty + 8 * os);
             umma_commit(bar_raw_empty + 8 * rs);

@@ -153,7 +153,8 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     if (elect_one()) {
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0, it = 0;
-      const uint64_t desc_e0 = make_smem_desc(sbase + kOffOp, kLBO), desc_hi0 = make_smem_desc(sbase + kOffOp + kHiOff, kLBO);
+      const uint32_t desc_e0 = (uint32_t)make_smem_desc(sbase + kOffOp, kLBO), desc_hi0 = (uint32_t)make_smem_desc(sbase + kOffOp + kHiOff, kLBO);
+      constexpr uint32_t kDescHi = (uint32_t)((((uint64_t)(kOpSBO >> 4) << 32) | (1ull << 46)) >> 32);   // high word: constant
       while (it < my_tiles) {
 #pragma unroll
         for (int os = 0; os < kOps; ++os) {
@@ -167,10 +168,10 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // descriptors of other stages / K steps differ by a constant in the address field (no carry: addresses < 2^18)
 #pragma unroll
             for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-              const uint64_t step = (uint64_t)((os * kOpBytes + k2 * 2 * kLBO) >> 4);
-              umma_ts(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi0 + step, idesc_k(144),
+              const uint32_t step = (uint32_t)((os * kOpBytes + k2 * 2 * kLBO) >> 4);
+              umma_ts32<kDescHi>(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi0 + step, idesc_k(144),
                       (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                         // [G | Eb] += hi^T [hi | E]
-              umma_ts(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e0 + step, idesc_k(144), 1u);
+              umma_ts32<kDescHi>(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e0 + step, idesc_k(144), 1u);
                                                                                                     // [Ea | G] += 2 lo^T [E | hi]
             }
             umma_commit(bar_op_empty + 8 * os);
