@@ -62,14 +62,6 @@ __host__ __device__ constexpr uint32_t idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(id), "r"(accumulate)
-      : "memory");
-}
 // One lane of a converged warp.  ptxas treats a region guarded by elect.sync as single-threaded: the tcgen05.mma / TMA
 // instructions inside compile to back-to-back uniform-datapath instructions with their operands in uniform registers.
 // Guarded by `lane == 0` instead, every one of them is wrapped in an ELECT / BRA.U.ANY waterfall loop behind a chain of
@@ -80,16 +72,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // the same with the descriptor as (runtime low word, compile-time high word): one register per MMA instead of two
-template <uint32_t DESC_HI>
-__device__ __forceinline__ void umma_ts32(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t id, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 d, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "r"(bdesc_lo), "r"(id), "r"(accumulate), "n"(DESC_HI)
-      : "memory");
-}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -146,6 +128,58 @@ __device__ __forceinline__ void wait_lean(uint32_t bar, uint32_t parity) {
       else if (now - t0 > 4000000000ull) __trap();
     }
   }
+}
+
+// Wait for two barriers at once: both try_wait are in flight together (an already-complete try_wait still takes ~90+
+// cycles; two in a row were ~a fifth of a transform warp's tile time).  Bounded like wait_lean.
+__device__ __forceinline__ void wait_lean2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t da, db;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3, %6;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5, %6;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(da), "=r"(db)
+      : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b), "r"(20000u)
+      : "memory");
+  if (!da) wait_lean(bar_a, par_a);
+  if (!db) wait_lean(bar_b, par_b);
+}
+// One tile of the issue thread in a single asm block: 4 MMAs, the two commits that free the A stage and the raw stage,
+// and -- after the first MMA -- a NON-BLOCKING probe of the next tile's `full` barrier whose result is consumed only after
+// the last MMA (mbarrier.test_wait takes 150-250 cycles here; every cycle this thread waits between two MMAs is a cycle
+// the tensor core idles, tools/ubench_umma.cu, so the probe has to be in flight while the MMAs issue).
+template <uint32_t DESC_HI, uint32_t IDESC>
+__device__ __forceinline__ bool issue_tile_single(uint32_t tmem_acc, uint32_t tmem_a, uint32_t desc, uint32_t first_accumulates,
+                                                  uint32_t bar_op_empty, uint32_t bar_raw_empty, uint32_t bar_next,
+                                                  uint32_t par_next) {
+  uint32_t ready;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pa, pt, pr;\n\t"
+      ".reg .b32 dl, ta;\n\t"
+      ".reg .b64 dd;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "mov.b64 dd, {%3, %9};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], dd, %10, pa;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pr, [%7], %8;\n\t"
+      "add.u32 dl, %3, 128;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %2, 8;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      "add.u32 dl, %3, 256;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %2, 16;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      "add.u32 dl, %3, 384;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %2, 24;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "selp.u32 %0, 1, 0, pr;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(tmem_acc), "r"(tmem_a), "r"(desc), "r"(first_accumulates), "r"(bar_op_empty), "r"(bar_raw_empty), "r"(bar_next),
+        "r"(par_next), "n"(DESC_HI), "n"(IDESC)
+      : "memory");
+  return ready != 0;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -232,13 +266,15 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       if (++s == kRaw) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: ONE elected thread runs the whole loop, unrolled over the raw stages so that every descriptor,
-    // tensor-memory address and barrier address is a constant offset from a loop-invariant uniform register: the path
-    // from "last MMA of tile t issued" to "first MMA of tile t+1 issued" must be shorter than the tensor core's queue =====
-    static_assert(kRaw % kOps == 0 || kOps == 4, "stage bookkeeping below assumes kOps = 4");
+    // ===== MMA issuer: ONE elected thread runs the whole loop.  The tensor core does not queue: tools/ubench_umma.cu shows
+    // that every cycle the issuing thread spends between two tcgen05.mma beyond ~one MMA time is a cycle the tensor core
+    // idles (bursts of 8 MMAs + commit + d cycles of other work take 648 + d cycles).  So the loop is unrolled over the
+    // stages (descriptors, tensor-memory and barrier addresses are constants off loop-invariant registers) and the
+    // readiness of the NEXT tile is probed between the MMAs of the current one, where the latency is free =====
     if (elect_one()) {
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0, it = 0, os = 0;
+      bool ready = false;
       const uint32_t desc00 = (uint32_t)make_desc_mn128(sbase + kOffRaw);      // low word; the high word is a constant
       constexpr uint32_t kDescHi = (uint32_t)((((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61)) >> 32);
       while (it < my_tiles) {
@@ -247,22 +283,21 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           if (it < my_tiles) {
             const int b = chunk & 1;
             if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-            wait_lean(bar_op_full + 8 * os, oph);     // implies raw_full of this tile (the producers waited for it)
+            if (!ready) wait_lean(bar_op_full + 8 * os, oph);     // implies raw_full of this tile (the producers waited for it)
             tc_fence_after();
             const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
             const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
             const uint32_t a_hi = tmem_base + kTmemAHi + (uint32_t)(os * 32);
-            // K steps of 16 rows are 2048 bytes apart inside the atoms, stages kRawBytes (no carry into other fields)
-#pragma unroll
-            for (int k2 = 0; k2 < kTcRows / 16; ++k2)
-              umma_ts32<kDescHi>(tmem_acc, a_hi + (uint32_t)(k2 * 8), desc00 + (uint32_t)((rs * kRawBytes + k2 * 2048) >> 4), idesc(144),
-                      (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                          // D += hi^T [x | E]
-            umma_commit(bar_op_empty + 8 * os);
-            umma_commit(bar_raw_empty + 8 * rs);
+            const int osn = (os + 1 == kOps) ? 0 : os + 1;
+            const uint32_t ophn = (os + 1 == kOps) ? (oph ^ 1u) : oph;
+            // K steps of 16 rows are 2048 bytes (128 descriptor units) apart inside the atoms, stages kRawBytes apart
+            ready = issue_tile_single<kDescHi, idesc(144)>(tmem_acc, a_hi, desc00 + (uint32_t)((rs * kRawBytes) >> 4),
+                                                          in_chunk > 0 ? 1u : 0u, bar_op_empty + 8 * os, bar_raw_empty + 8 * rs,
+                                                          bar_op_full + 8 * osn, ophn);
             if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
             else ++in_chunk;
             ++it;
-            if (++os == kOps) { os = 0; oph ^= 1; }
+            os = osn; oph = ophn;
           }
         }
       }
@@ -278,8 +313,7 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int rr = lane + 32 * (warp - 2);
     const uint32_t e_off = kRawX + (uint32_t)rr * 128u + ((uint32_t)(rr & 7) << 4);
     for (int it = 0; it < my_tiles; ++it) {
-      wait_lean(bar_raw_full + 8 * rs, rph);
-      wait_lean(bar_op_empty + 8 * os, oph ^ 1);
+      wait_lean2(bar_raw_full + 8 * rs, rph, bar_op_empty + 8 * os, oph ^ 1);
       const int64_t left = n_rows - (tile_begin + it) * kTcRows;
       bool use = rr < left;
       if (use && has_mask) use = (ld_shared_u8(sbase + kOffMask + rs * kMBytes + rr) == (uint32_t)keep);
@@ -379,8 +413,7 @@ gram_b16_single_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      wait_lean(bar_raw_full + 8 * rs, rph);
-      wait_lean(bar_op_empty + 8 * os, oph ^ 1);
+      wait_lean2(bar_raw_full + 8 * rs, rph, bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
       const uint32_t stage = sbase + kOffRaw + rs * kRawBytes;
       const uint32_t raw_addr = stage + lm_off + (uint32_t)(2 * s) * 1024u;

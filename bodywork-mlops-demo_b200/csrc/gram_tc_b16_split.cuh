@@ -56,6 +56,57 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
                ::"r"(taddr), "r"(0u) : "memory");
 }
 
+// One tile of the issue thread in a single asm block: 8 MMAs (stage OS), the commit that frees the stage, and -- after
+// the first K step -- a NON-BLOCKING probe of the next tile's `full` barrier whose result is consumed only after the last
+// MMA: mbarrier.test_wait takes 150-250 cycles here, and every cycle this thread waits between two MMAs is a cycle the
+// tensor core idles (tools/ubench_umma.cu), so the probe has to be in flight while the MMAs issue.
+template <uint32_t DESC_HI, uint32_t IDESC>
+__device__ __forceinline__ bool issue_tile(uint32_t tmem_acc, uint32_t tmem_a, uint32_t desc_hi, uint32_t desc_e,
+                                           uint32_t first_accumulates, uint32_t bar_empty, uint32_t bar_next, uint32_t par_next) {
+  uint32_t ready;
+  constexpr uint32_t kSK = (uint32_t)((2 * kLBO) >> 4);          // descriptor step of one K = 16 step
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pa, pt, pr;\n\t"
+      ".reg .b32 dl, ta, td;\n\t"
+      ".reg .b64 dd;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, %4, %4;\n\t"
+      "add.u32 td, %1, 16;\n\t"
+      // K step 0
+      "mov.b64 dd, {%2, %9};\n\t add.u32 ta, %5, %11;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [td], [ta], dd, %10, pa;\n\t"
+      "mov.b64 dd, {%3, %9};\n\t add.u32 ta, %5, %15;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pr, [%6], %7;\n\t"
+      // K step 1
+      "add.u32 dl, %2, %19;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %12;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [td], [ta], dd, %10, pt;\n\t"
+      "add.u32 dl, %3, %19;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %16;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      // K step 2
+      "add.u32 dl, %2, %20;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %13;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [td], [ta], dd, %10, pt;\n\t"
+      "add.u32 dl, %3, %20;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %17;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      // K step 3
+      "add.u32 dl, %2, %21;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %14;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [td], [ta], dd, %10, pt;\n\t"
+      "add.u32 dl, %3, %21;\n\t mov.b64 dd, {dl, %9};\n\t add.u32 ta, %5, %18;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], dd, %10, pt;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+      "selp.u32 %0, 1, 0, pr;\n\t"
+      "}"
+      : "=r"(ready)
+      : "r"(tmem_acc), "r"(desc_hi), "r"(desc_e), "r"(first_accumulates), "r"(tmem_a), "r"(bar_next), "r"(par_next),
+        "r"(bar_empty), "n"(DESC_HI), "n"(IDESC),
+        "n"(kTmemAHi), "n"(kTmemAHi + 8), "n"(kTmemAHi + 16), "n"(kTmemAHi + 24),
+        "n"(kTmemALo), "n"(kTmemALo + 8), "n"(kTmemALo + 16), "n"(kTmemALo + 24),
+        "n"(kSK), "n"(2 * kSK), "n"(3 * kSK)
+      : "memory");
+  return ready != 0;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ CUtensorMap tmM, int y_map_2d, int has_mask, int keep, int64_t n_rows,
@@ -147,12 +198,14 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == kRaw) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: ONE elected thread runs the whole loop, unrolled over the operand stages so that every descriptor,
-    // tensor-memory address and barrier address is a constant offset from a loop-invariant uniform register: the path
-    // from "last MMA of tile t issued" to "first MMA of tile t+1 issued" must be shorter than the tensor core's queue =====
+    // ===== MMA issuer: ONE elected thread runs the whole loop.  The tensor core does not queue: every cycle the issuing
+    // thread spends between two tcgen05.mma beyond ~one MMA time is a cycle the tensor core idles (tools/ubench_umma.cu).
+    // So the loop is unrolled over the operand stages (descriptors, tensor-memory and barrier addresses are constants
+    // off loop-invariant registers) and the readiness of the NEXT tile is probed between the MMAs of the current one =====
     if (elect_one()) {
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0, it = 0;
+      bool ready = false;
       const uint32_t desc_e0 = (uint32_t)make_smem_desc(sbase + kOffOp, kLBO), desc_hi0 = (uint32_t)make_smem_desc(sbase + kOffOp + kHiOff, kLBO);
       constexpr uint32_t kDescHi = (uint32_t)((((uint64_t)(kOpSBO >> 4) << 32) | (1ull << 46)) >> 32);   // high word: constant
       while (it < my_tiles) {
@@ -161,20 +214,16 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           if (it < my_tiles) {
             const int b = chunk & 1;
             if (in_chunk == 0) wait_lean(bar_acc_empty + 8 * b, ((chunk >> 1) & 1) ^ 1);
-            wait_lean(bar_op_full + 8 * os, oph);
+            if (!ready) wait_lean(bar_op_full + 8 * os, oph);
             tc_fence_after();
             const bool last = (in_chunk == chunk_tiles - 1) || (it == my_tiles - 1);
             const uint32_t tmem_acc = tmem_base + (uint32_t)b * kAccStride;
+            const int osn = (os + 1 == kOps) ? 0 : os + 1;
+            const uint32_t ophn = (os + 1 == kOps) ? (oph ^ 1u) : oph;
             // descriptors of other stages / K steps differ by a constant in the address field (no carry: addresses < 2^18)
-#pragma unroll
-            for (int k2 = 0; k2 < kTcRows / 16; ++k2) {
-              const uint32_t step = (uint32_t)((os * kOpBytes + k2 * 2 * kLBO) >> 4);
-              umma_ts32<kDescHi>(tmem_acc + 16, tmem_base + kTmemAHi + (uint32_t)(os * 32 + k2 * 8), desc_hi0 + step, idesc_k(144),
-                      (in_chunk > 0 || k2 > 0) ? 1u : 0u);                                         // [G | Eb] += hi^T [hi | E]
-              umma_ts32<kDescHi>(tmem_acc, tmem_base + kTmemALo + (uint32_t)(os * 32 + k2 * 8), desc_e0 + step, idesc_k(144), 1u);
-                                                                                                    // [Ea | G] += 2 lo^T [E | hi]
-            }
-            umma_commit(bar_op_empty + 8 * os);
+            ready = issue_tile<kDescHi, idesc_k(144)>(tmem_acc, tmem_base + (uint32_t)(os * 32), desc_hi0 + (uint32_t)((os * kOpBytes) >> 4),
+                                                     desc_e0 + (uint32_t)((os * kOpBytes) >> 4), in_chunk > 0 ? 1u : 0u,
+                                                     bar_op_empty + 8 * os, bar_op_full + 8 * osn, ophn);
             if (last) { umma_commit(bar_acc_full + 8 * b); in_chunk = 0; ++chunk; }
             else ++in_chunk;
             ++it;
@@ -192,8 +241,7 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint32_t rph = 0, oph = 0;
     const int rr = lane + 32 * (warp - 2);
     for (int it = 0; it < my_tiles; ++it) {
-      wait_lean(bar_raw_full + 8 * rs, rph);
-      wait_lean(bar_op_empty + 8 * os, oph ^ 1);
+      wait_lean2(bar_raw_full + 8 * rs, rph, bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
       const int64_t left = n_rows - (tile_begin + it) * kTcRows;
       bool use = rr < left;
@@ -295,8 +343,7 @@ gram_b16_split_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      wait_lean(bar_raw_full + 8 * rs, rph);
-      wait_lean(bar_op_empty + 8 * os, oph ^ 1);
+      wait_lean2(bar_raw_full + 8 * rs, rph, bar_op_empty + 8 * os, oph ^ 1);
       tc_fence_after();
       const uint32_t raw_addr = sbase + kOffRaw + rs * kRawBytes + lm_off + (uint32_t)(2 * s) * 1024u;
       uint32_t R[2][4];

@@ -66,8 +66,11 @@ __global__ void __launch_bounds__(128, 1) k(int n_cols, int mode, int reps, long
             if (mode & 1) mma_ss(d, make_desc(sbase + st + k2 * 2 * lbo + 20480u, lbo), b, id, 1u);
             else mma_ts(d, tb + 480 + k2 * 8, b, id, 1u);
           }
-          if (commit_every > 0 && (r % commit_every) == commit_every - 1)     // a pipeline stage hand-off, nobody waits on it
+          if (commit_every > 0 && (r & 1)) {          // every 8 MMAs: a stage hand-off (nobody waits on it) + `commit_every - 1`
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+            const long long t_end = clock64() + (commit_every - 1);      // cycles of issue-thread work before the next MMA
+            while (clock64() < t_end) {}
+          }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
       }
@@ -112,15 +115,15 @@ int main() {
     }
   }
   // tcgen05.commit between groups of MMAs (as a pipelined kernel issues them: one or two per tile of 4 or 8 MMAs)
-  for (int ce : {0, 4, 2, 1}) {
-    printf("grid 148  A tmem  N144  commit every %d MMAs :", ce * 4);
+  for (int ce : {0, 1, 51, 101, 151, 201, 301, 401, 601}) {
+    printf("grid 148  N144  bursts of 8 MMAs + commit + %3d cycles of issue-thread delay :", ce > 0 ? ce - 1 : -1);
     for (int mode : {0, 1}) {
       k<<<148, 128, smem>>>(144, mode, reps, out, ce);
       long long h[148];
       cudaMemcpy(h, out, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
       long long mx = 0;
       for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
-      printf("  %s %5.1f cycles / MMA", mode ? "A smem" : "A tmem", (double)mx / (reps * 4));
+      printf("  %s %6.1f cycles / burst", mode ? "A smem" : "A tmem", (double)mx / (reps / 2));
     }
     printf("\n");
   }
