@@ -444,8 +444,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one elected thread: straight-line UTCHMMA, see elect_one) =====
+    if (elect_one()) {
       int os = 0;
       uint32_t oph = 0;
       int in_chunk = 0, chunk = 0;
