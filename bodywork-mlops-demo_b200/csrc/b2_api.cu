@@ -163,8 +163,16 @@ int ensure_bounce(b2_ctx* ctx) {
 }
 
 void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_bytes, size_t src_pitch) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)(hw == 0 ? 4 : (hw > 8 ? 8 : hw));
+  // copy threads: half the hardware threads, at most 16 (measured on the 64-thread GPU box, tools/perf_pageable.py);
+  // B2_COPY_THREADS overrides
+  static const int nt_cfg = []() {
+    const char* e = getenv("B2_COPY_THREADS");
+    if (e != nullptr && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int half = (int)(hw / 2);
+    return half < 4 ? 4 : (half > 16 ? 16 : half);
+  }();
+  int nt = nt_cfg;
   if ((size_t)rows * row_bytes < ((size_t)8 << 20)) nt = 1;
   auto work = [=](int t) {
     const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
