@@ -227,6 +227,16 @@ def max_over_ranks(dist, value: float) -> float:
     return float(t.item())
 
 
+def gather_ranks(dist, value: float):
+    """`value` of every rank (gloo all-gather), rank order; None on one GPU."""
+    if dist is None:
+        return None
+    import torch
+    out = [torch.zeros(1, dtype=torch.float64) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, torch.tensor([value], dtype=torch.float64))
+    return [round(float(t.item()), 5) for t in out]
+
+
 def time_fits(ctx, dist, X, y, steps: int, warmup: int, barrier):
     """`steps` complete fits (b2_fit: Gram + exchange + solve, coefficients on the host), CUDA-event timed, max over
     ranks.  Returns (ms_total, gram_kernel_ms_avg, launches, last (coef, intercept))."""
@@ -393,6 +403,8 @@ def main() -> None:
     kernel_ms, kernel_launches = ctx.last_kernel_ms()
     launches = ctx.launch_count() - launches0
     fused_fits = ctx.stats()["fused_fits"] - fused0
+    step_ms_by_rank = gather_ranks(dist, ms / args.steps)
+    kernel_ms_by_rank = gather_ranks(dist, kernel_ms / max(kernel_launches, 1))
     ms = max_over_ranks(dist, ms)
 
     total_rows = rows * world
@@ -407,6 +419,10 @@ def main() -> None:
                 "step_tail_us": 1e3 * (ms / args.steps - gram_ms),
                 "whole_fit_frac_of_hbm_peak": rows * bytes_per_row / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "traffic": ncu_traffic_per_launch(f"{kind}_{rows}x{D}")}
+    if kernel_ms_by_rank is not None:      # the step waits for the slowest rank: its kernel, not rank 0's, sets the tail
+        roofline["kernel_ms_by_rank"] = kernel_ms_by_rank
+        roofline["step_ms_by_rank"] = step_ms_by_rank
+        roofline["step_tail_us_vs_slowest_kernel"] = 1e3 * (ms / args.steps - max(kernel_ms_by_rank))
     info = ctx.comm_info()
     exchange = {"exchange_used": info["exchange"], "n_ranks": info["n_ranks"], "note": exchange_note,
                 "fused_fits": fused_fits, "of_steps": args.steps,
