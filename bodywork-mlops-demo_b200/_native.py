@@ -53,6 +53,7 @@ _SIGNATURES = {
     "b2_gram_export": (C.c_int, [_vp, _vp, C.POINTER(_c_i64)]),
     "b2_gram_import": (C.c_int, [_vp, _vp, C.c_int]),
     "b2_split_mask": (C.c_int, [_c_i64, _c_i64, C.c_uint32, _vp]),
+    "b2_upload_columns": (C.c_int, [_vp, _vp, _vp, C.c_int, _c_i64, C.c_int, _vp]),
     "b2_fit": (C.c_int, [_vp, _vp, C.c_int, _vp, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp,
                          C.POINTER(C.c_double)]),
     "b2_solve": (C.c_int, [_vp, C.c_double, C.c_int, _vp, C.POINTER(C.c_double)]),
@@ -283,6 +284,22 @@ class Context:
             kind = {np.dtype(np.float32): "f32", np.dtype(np.uint16): "bf16", np.dtype(np.uint8): "u8",
                     np.dtype(np.float64): "f64"}[host.dtype]
         return DeviceArray(self, host.shape, kind).copy_from(host)
+
+    def upload_columns(self, columns) -> DeviceArray:
+        """1-D host columns (all float64 or all float32, any stride -- what ``DataFrame[c].to_numpy()`` returns) -> a
+        row-major float32 (n, d) DeviceArray: gathered, converted and copied by ``b2_upload_columns`` (host threads + a
+        pinned ring), without the transposing copy / conversion passes of ``DataFrame.to_numpy``."""
+        cols = [np.asarray(c) for c in columns]
+        if not cols or any(c.ndim != 1 or c.shape != cols[0].shape or c.dtype != cols[0].dtype for c in cols) \
+                or cols[0].dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise RuntimeError("upload_columns: 1-D columns of one length and one dtype (float64 or float32) expected")
+        n, d = int(cols[0].shape[0]), len(cols)
+        out = DeviceArray(self, (n, d), "f32")
+        ptrs = (C.c_void_p * d)(*[c.ctypes.data for c in cols])
+        strides = (C.c_int64 * d)(*[c.strides[0] if n > 1 else c.itemsize for c in cols])
+        _check(load().b2_upload_columns(self._h, C.cast(ptrs, C.c_void_p), C.cast(strides, C.c_void_p),
+                                        F64 if cols[0].dtype == np.float64 else F32, n, d, out.ptr), "b2_upload_columns")
+        return out
 
     def pinned(self, shape, dtype) -> PinnedArray:
         return PinnedArray(self, tuple(np.atleast_1d(shape)), dtype)

@@ -162,9 +162,7 @@ int ensure_bounce(b2_ctx* ctx) {
   return B2_OK;
 }
 
-void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_bytes, size_t src_pitch) {
-  // copy threads: half the hardware threads, at most 16 (measured on the 64-thread GPU box, tools/perf_pageable.py);
-  // B2_COPY_THREADS overrides
+static int copy_threads() {
   static const int nt_cfg = []() {
     const char* e = getenv("B2_COPY_THREADS");
     if (e != nullptr && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
@@ -172,7 +170,13 @@ void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_byt
     const int half = (int)(hw / 2);
     return half < 4 ? 4 : (half > 16 ? 16 : half);
   }();
-  int nt = nt_cfg;
+  return nt_cfg;
+}
+
+void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_bytes, size_t src_pitch) {
+  // copy threads: half the hardware threads, at most 16 (measured on the 64-thread GPU box, tools/perf_pageable.py);
+  // B2_COPY_THREADS overrides
+  int nt = copy_threads();
   if ((size_t)rows * row_bytes < ((size_t)8 << 20)) nt = 1;
   auto work = [=](int t) {
     const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
@@ -188,6 +192,25 @@ void parallel_copy_rows(char* dst, const char* src, int64_t rows, size_t row_byt
   for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
   work(0);
   for (auto& th : pool) th.join();
+}
+
+// gather + convert `rows` rows of d strided host columns into a row-major fp32 block (b2_upload_columns)
+template <typename T>
+static void pack_rows(float* dst, const void* const* cols, const int64_t* strides, int64_t r0, int64_t rows, int d) {
+  constexpr int kRowsPerTile = 64, kColsPerPass = 16;
+  for (int64_t t0 = 0; t0 < rows; t0 += kRowsPerTile) {
+    const int64_t tr = rows - t0 < kRowsPerTile ? rows - t0 : kRowsPerTile;
+    for (int j0 = 0; j0 < d; j0 += kColsPerPass) {
+      const int jc = d - j0 < kColsPerPass ? d - j0 : kColsPerPass;
+      const char* src[kColsPerPass];
+      int64_t st[kColsPerPass];
+      for (int j = 0; j < jc; ++j) { st[j] = strides[j0 + j]; src[j] = static_cast<const char*>(cols[j0 + j]) + (r0 + t0) * st[j]; }
+      for (int64_t r = 0; r < tr; ++r) {
+        float* out = dst + (size_t)(t0 + r) * d + j0;
+        for (int j = 0; j < jc; ++j) out[j] = (float)*reinterpret_cast<const T*>(src[j] + r * st[j]);
+      }
+    }
+  }
 }
 
 // copy rows [r0, r0+rows) of a host matrix into a compact (ldx == d) staging block
@@ -418,6 +441,52 @@ int b2_copy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   return B2_OK;
 }
+// ---- DataFrame columns -> row-major fp32 rows in HBM --------------------------------------------------------------------
+// pandas keeps every column of `data` as its own strided array; `data[cols].to_numpy(dtype=float32)` + ascontiguousarray
+// is two single-threaded passes (a transposing copy and a conversion) and then a pageable H2D copy -- 90 % of train_model's
+// time once the fit takes a millisecond.  Here the host threads of the bounce ring gather 16 columns at a time into the
+// pinned bounce block (full 64-byte lines written, every column read as its own sequential stream), converting on the fly,
+// while the previous block is on the wire.
+int b2_upload_columns(b2_ctx* ctx, const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d,
+                      float* X_dev) {
+  if (int r = use_device(ctx)) return r;
+  if (cols == nullptr || strides == nullptr || X_dev == nullptr || n_rows < 0 || d < 1 || d > kMaxD ||
+      (dtype != B2_F32 && dtype != B2_F64)) {
+    set_error("b2_upload_columns: bad arguments (1 <= d <= %d, dtype B2_F32 or B2_F64)", kMaxD);
+    return B2_E_ARG;
+  }
+  for (int j = 0; j < d; ++j)
+    if (cols[j] == nullptr) { set_error("b2_upload_columns: column %d is null", j); return B2_E_ARG; }
+  if (int r = ensure_staging(ctx)) return r;
+  if (int r = ensure_bounce(ctx)) return r;
+  const int nt = copy_threads();
+  int buf = 0;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += ctx->stage_rows, buf ^= 1) {
+    const int64_t rows = n_rows - r0 < ctx->stage_rows ? n_rows - r0 : ctx->stage_rows;
+    B2_CUDA(cudaEventSynchronize(ctx->ev_bounce[buf]));               // the H2D that last read this bounce block is done
+    float* dst = static_cast<float*>(ctx->bounce[buf]);
+    auto work = [=](int t) {
+      const int64_t lo = rows * t / nt / 64 * 64, hi = (t == nt - 1) ? rows : rows * (t + 1) / nt / 64 * 64;
+      if (hi <= lo) return;
+      if (dtype == B2_F64) pack_rows<double>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
+      else pack_rows<float>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
+    };
+    if (rows < 4096 || nt == 1) {
+      if (dtype == B2_F64) pack_rows<double>(dst, cols, strides, r0, rows, d); else pack_rows<float>(dst, cols, strides, r0, rows, d);
+    } else {
+      std::vector<std::thread> pool;
+      pool.reserve(nt - 1);
+      for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+      work(0);
+      for (auto& th : pool) th.join();
+    }
+    B2_CUDA(cudaMemcpyAsync(X_dev + (size_t)r0 * d, dst, (size_t)rows * d * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    B2_CUDA(cudaEventRecord(ctx->ev_bounce[buf], ctx->copy_stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  return B2_OK;
+}
+
 int b2_copy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (int r = use_device(ctx)) return r;
   B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -214,19 +214,26 @@ def train_model(data: pd.DataFrame):
     Numeric contract: the rows are staged as float32 (what the kernels stream; the reference keeps pandas' float64),
     sums, solve, predictions and metric reductions are float64 -- coefficients agree with the reference's to ~1e-6
     relative, metrics to ~1e-7 (asserted against fixtures produced by the unmodified reference)."""
+    columns = None
     if isinstance(data, TrancheRows):
         X, y = data.X, data.y                  # pinned, fp32, straight from the tranche files
+        n = X.shape[0]
     else:
-        cols = feature_columns(data)
-        X = np.ascontiguousarray(data[cols].to_numpy(dtype=np.float32))
+        # a DataFrame holds every column as its own strided array: hand the columns to b2_upload_columns (host threads
+        # gather + convert into a pinned ring beside the H2D copies) instead of DataFrame.to_numpy's transposing copy
+        columns = [data[c].to_numpy() for c in feature_columns(data)]
+        if len({c.dtype for c in columns}) != 1 or columns[0].dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            X = np.ascontiguousarray(np.stack(columns, axis=1), dtype=np.float32)
+            columns = None
         y = np.ascontiguousarray(data["y"].to_numpy(dtype=np.float32))
-    n = X.shape[0]
+        n = y.shape[0]
     mask_job = split_mask_async(n)             # O(n) host shuffle, beside the copies below
 
     ctx = default_context()
     Xd = yd = md = None
     try:
-        Xd, yd = ctx.to_device(X), ctx.to_device(y)
+        Xd = ctx.upload_columns(columns) if columns is not None else ctx.to_device(X)
+        yd = ctx.to_device(y)
         md = ctx.to_device(mask_job.result())
         reg = B200LinearRegression(fit_intercept=True, ctx=ctx)
         reg.fit(Xd, yd, row_mask=md, mask_keep=1)

@@ -36,7 +36,7 @@ extern "C" {
 /* element type of X */
 #define B2_F32 0
 #define B2_BF16 1
-#define B2_F64 2 /* b2_metrics only */
+#define B2_F64 2 /* b2_metrics, b2_upload_columns */
 
 /* where a caller buffer lives */
 #define B2_MEM_DEVICE 0 /* device pointer (HBM)                                   */
@@ -95,6 +95,13 @@ int b2_host_free(b2_ctx* ctx, void* p);
 int b2_copy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
 int b2_copy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
 int b2_dev_memset(b2_ctx* ctx, void* dst, int value, size_t bytes);
+/* DataFrame columns -> row-major float32 rows in HBM.  reference: stage_1_train_model.py:95-96
+ * (`X = data['X'].values.reshape(-1, 1)`): pandas hands every column over as its own strided array.  cols[j] = address of
+ * row 0 of feature column j, strides[j] = bytes between consecutive rows of it, dtype = B2_F64 (pandas' default) or B2_F32;
+ * X_dev: caller-owned device buffer of n_rows x d floats, row-major.  Host threads gather and convert into a pinned ring
+ * while the previous block is on the wire; sync on return. */
+int b2_upload_columns(b2_ctx* ctx, const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d,
+                      float* X_dev);
 
 /* ---- Gram accumulation: replaces LinearRegression.fit's pass over the rows -----------------
  * reference: stage_1_train_model.py:105-106 -> sklearn/linear_model/_base.py (centre + gelsd). */

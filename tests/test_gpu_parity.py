@@ -857,3 +857,44 @@ def test_non_finite_input_is_refused_like_sklearn(ctx):
         b2.B200LinearRegression(ctx=ctx).fit(X, y)
     y[5] = 0.0
     assert np.all(np.isfinite(b2.B200LinearRegression(ctx=ctx).fit(X, y).coef_))     # the context is still usable
+
+
+# ------------------------------------------------------------------------------------------------
+# DataFrame columns -> device rows (b2_upload_columns): the gather + conversion train_model uses
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,dtype", [(1, 1, np.float64), (1000, 3, np.float64), (70_001, 128, np.float64),
+                                       (300_000, 40, np.float32), (263_000, 128, np.float64)])
+def test_upload_columns_equals_numpy_conversion(ctx, n, d, dtype):
+    """Strided float64 / float32 columns (a consolidated pandas block, a Fortran-ordered array, every other element of a
+    longer vector) arrive as exactly ``np.stack(columns, 1).astype(float32)``, across the 262 144-row bounce blocks."""
+    rng = np.random.RandomState(n + d)
+    block = (rng.rand(d, n) * 100).astype(dtype)                  # pandas: one (d, n) block, columns contiguous
+    cols = [block[j] for j in range(d)]
+    if d >= 3:
+        wide = (rng.rand(2 * n) * 100).astype(dtype)
+        cols[1] = wide[::2]                                        # a strided column
+        cols[2] = np.asfortranarray(rng.rand(n, 2).astype(dtype))[:, 1]
+    Xd = ctx.upload_columns(cols)
+    got = Xd.to_host()
+    Xd.free()
+    assert got.shape == (n, d) and got.dtype == np.float32
+    assert np.array_equal(got, np.stack(cols, axis=1).astype(np.float32))
+    with pytest.raises(RuntimeError):
+        ctx.upload_columns([cols[0], cols[0][:-1]] if n > 1 else [np.zeros(3, np.int32)])
+
+
+def test_train_model_takes_dataframe_columns_without_a_host_copy(ctx, monkeypatch):
+    """train_model(DataFrame) must not materialise the (n, d) matrix on the host: the columns go to b2_upload_columns."""
+    import pandas as pd
+    X, y = orc.generate_dataset(50_000, 16, seed=5, dtype=np.float64)
+    df = pd.DataFrame({"date": "2021-01-01", "y": y, **{f"X{j}": X[:, j] for j in range(16)}})
+
+    def no_stack(*a, **k):
+        raise AssertionError("train_model stacked the columns on the host")
+    monkeypatch.setattr(np, "stack", no_stack)
+    model, metrics = s1.train_model(df)
+    monkeypatch.undo()
+    mask = s1.split_mask(len(y))
+    ref = orc.fit_from_stats(orc.gram_stats(X[mask == 1].astype(np.float32), y[mask == 1].astype(np.float32)))
+    assert np.max(np.abs(model.coef_ - ref["coef"])) < COEF_TOL
+    assert 0.9 < float(metrics["r_squared"][0]) <= 1.0
