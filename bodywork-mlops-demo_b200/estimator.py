@@ -28,6 +28,9 @@ def default_context() -> native.Context:
     return _shared_ctx
 
 
+_F64_UPLOAD_LIMIT = 64 << 30     # float64 host rows larger than this (as fp32, bytes) are converted and streamed block-wise
+
+
 def _as_f32_matrix(X) -> np.ndarray:
     X = np.asarray(X)
     if X.ndim == 1:
@@ -91,14 +94,30 @@ class B200LinearRegression:
         ``row_mask`` (uint8 per row) restricts the fit to rows equal to ``mask_keep``.
         ``with_spectrum=False`` defers ``singular_`` / ``rank_`` (computed on first use, e.g. by ``to_sklearn``)."""
         ctx = self.ctx
+        owned = []                  # device buffers this call created (float64 host rows: converted on the way up)
         if isinstance(X, native.DeviceArray):
             d = X.shape[1]
         else:
-            X = _as_f32_matrix(X)
-            y = np.ascontiguousarray(np.asarray(y).ravel(), dtype=np.float32)
-            if y.shape[0] != X.shape[0]:
-                raise ValueError(f"Found input variables with inconsistent numbers of samples: "
-                                 f"[{X.shape[0]}, {y.shape[0]}]")
+            Xh = np.asarray(X)
+            if Xh.ndim == 2 and Xh.dtype == np.float64 and 0 < Xh.shape[1] <= native.MAX_D and Xh.shape[0] >= 65_536 \
+                    and Xh.size * 4 <= _F64_UPLOAD_LIMIT:
+                # what scikit-learn users hand over: float64 rows.  numpy's astype(float32) is one thread; b2_upload_columns
+                # converts with the host threads of the bounce ring beside the H2D copies and leaves the rows resident
+                if np.asarray(y).size != Xh.shape[0]:
+                    raise ValueError(f"Found input variables with inconsistent numbers of samples: "
+                                     f"[{Xh.shape[0]}, {np.asarray(y).size}]")
+                X = ctx.upload_columns([Xh[:, j] for j in range(Xh.shape[1])])
+                y = ctx.to_device(np.ascontiguousarray(np.asarray(y).ravel(), dtype=np.float32))
+                owned = [X, y]
+                if row_mask is not None and not isinstance(row_mask, native.DeviceArray):
+                    row_mask = ctx.to_device(np.ascontiguousarray(row_mask, dtype=np.uint8))
+                    owned.append(row_mask)
+            else:
+                X = _as_f32_matrix(X)
+                y = np.ascontiguousarray(np.asarray(y).ravel(), dtype=np.float32)
+                if y.shape[0] != X.shape[0]:
+                    raise ValueError(f"Found input variables with inconsistent numbers of samples: "
+                                     f"[{X.shape[0]}, {y.shape[0]}]")
             d = X.shape[1]
         self._S = None
         self._drop_spectrum()
@@ -108,6 +127,9 @@ class B200LinearRegression:
             self._set_solution(coef, b0, d)
         except np.linalg.LinAlgError:
             singular = True         # rank deficient and alpha == 0: the minimum-norm solution gelsd would return
+        finally:
+            for a in owned:
+                a.free()
         self._serial = ctx.serial
         if with_spectrum or singular:
             self._spectrum(d, need_coef=singular)

@@ -898,3 +898,18 @@ def test_train_model_takes_dataframe_columns_without_a_host_copy(ctx, monkeypatc
     ref = orc.fit_from_stats(orc.gram_stats(X[mask == 1].astype(np.float32), y[mask == 1].astype(np.float32)))
     assert np.max(np.abs(model.coef_ - ref["coef"])) < COEF_TOL
     assert 0.9 < float(metrics["r_squared"][0]) <= 1.0
+
+
+def test_estimator_fit_on_float64_host_rows(ctx):
+    """float64 host rows (what scikit-learn users pass) are converted by b2_upload_columns on the way up and fitted
+    resident: same coefficients as the oracle's fit of the float32-rounded rows, masks honoured, buffers released."""
+    X, y = orc.generate_dataset(120_000, 32, seed=21, dtype=np.float64)
+    est = b2.B200LinearRegression(ctx=ctx).fit(X, y)
+    ref = orc.fit_from_stats(orc.gram_stats(X.astype(np.float32), y.astype(np.float32)))
+    assert np.max(np.abs(est.coef_ - ref["coef"])) < COEF_TOL and est.rank_ == 32
+    mask = (np.arange(len(y)) % 4 != 0).astype(np.uint8)
+    est2 = b2.B200LinearRegression(ctx=ctx).fit(np.asfortranarray(X), y, row_mask=mask, mask_keep=1)
+    ref2 = orc.fit_from_stats(orc.gram_stats(X[mask == 1].astype(np.float32), y[mask == 1].astype(np.float32)))
+    assert np.max(np.abs(est2.coef_ - ref2["coef"])) < COEF_TOL
+    with pytest.raises(ValueError):
+        b2.B200LinearRegression(ctx=ctx).fit(X, y[:-1])
