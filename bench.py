@@ -95,7 +95,8 @@ class ClockSampler:
             try:
                 self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
                                      nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
-                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                     nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)))
             except Exception:
                 break
             time.sleep(0.002)
@@ -122,8 +123,15 @@ class ClockSampler:
             mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
         except Exception:
             mx = None
+        mem = sorted(s[3] for s in self.samples)
+        try:
+            mem_mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_MEM)
+        except Exception:
+            mem_mx = None
+        # the HBM clock too: the Gram kernel's fraction of the (fixed) measured peak varies 0.8-0.97 box to box at equal SM clocks
         return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(mx) if mx else None, "samples": len(sm),
-                "power_w_max": max(s[2] for s in self.samples), "reasons": reasons, "how": "NVML poll, 2 ms"}
+                "power_w_max": max(s[2] for s in self.samples), "reasons": reasons, "how": "NVML poll, 2 ms",
+                "mem_mhz": float(mem[len(mem) // 2]), "mem_max_mhz": float(mem_mx) if mem_mx else None}
 
     def _smi_once(self) -> dict:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
