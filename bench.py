@@ -427,6 +427,12 @@ def main() -> None:
                 "step_tail_us": 1e3 * (ms / args.steps - gram_ms),
                 "whole_fit_frac_of_hbm_peak": rows * bytes_per_row / (ms / args.steps * 1e-3) / 1e9 / peak,
                 "traffic": ncu_traffic_per_launch(f"{kind}_{rows}x{D}")}
+    try:       # this box's own copy bandwidth next to the pool's figure: the fraction above varies 0.8-0.97 box to box
+        box = ctx.copy_bandwidth_gbs()
+        roofline["copy_gbs_this_gpu"] = box
+        roofline["frac_of_this_gpu_copy"] = achieved / box
+    except Exception:  # noqa: BLE001 - a diagnostic, never fatal
+        pass
     if kernel_ms_by_rank is not None:      # the step waits for the slowest rank: its kernel, not rank 0's, sets the tail
         roofline["kernel_ms_by_rank"] = kernel_ms_by_rank
         roofline["step_ms_by_rank"] = step_ms_by_rank

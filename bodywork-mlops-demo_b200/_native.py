@@ -53,6 +53,7 @@ _SIGNATURES = {
     "b2_gram_export": (C.c_int, [_vp, _vp, C.POINTER(_c_i64)]),
     "b2_gram_import": (C.c_int, [_vp, _vp, C.c_int]),
     "b2_split_mask": (C.c_int, [_c_i64, _c_i64, C.c_uint32, _vp]),
+    "b2_copy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "b2_upload_columns": (C.c_int, [_vp, _vp, _vp, C.c_int, _c_i64, C.c_int, _vp]),
     "b2_fit": (C.c_int, [_vp, _vp, C.c_int, _vp, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp,
                          C.POINTER(C.c_double)]),
@@ -300,6 +301,22 @@ class Context:
         _check(load().b2_upload_columns(self._h, C.cast(ptrs, C.c_void_p), C.cast(strides, C.c_void_p),
                                         F64 if cols[0].dtype == np.float64 else F32, n, d, out.ptr), "b2_upload_columns")
         return out
+
+    def copy_bandwidth_gbs(self, nbytes: int = 2 << 30, reps: int = 10) -> float:
+        """This GPU's device-to-device copy bandwidth (read + write bytes per second, GB/s, best of ``reps``) -- the quantity
+        MEASURED_PEAKS.json holds for the pool; boxes differ."""
+        a, b = DeviceArray(self, (nbytes,), "u8"), DeviceArray(self, (nbytes,), "u8")
+        try:
+            _check(load().b2_dev_memset(self._h, a.ptr, 1, nbytes), "b2_dev_memset")
+            best = 0.0
+            for _ in range(reps + 2):
+                self.sync(); self.timer_start()
+                _check(load().b2_copy_d2d(self._h, b.ptr, a.ptr, nbytes), "b2_copy_d2d")
+                ms = self.timer_stop()
+                best = max(best, 2.0 * nbytes / (ms * 1e-3) / 1e9)
+            return best
+        finally:
+            a.free(); b.free()
 
     def pinned(self, shape, dtype) -> PinnedArray:
         return PinnedArray(self, tuple(np.atleast_1d(shape)), dtype)

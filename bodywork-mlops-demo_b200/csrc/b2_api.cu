@@ -493,6 +493,11 @@ int b2_copy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
   B2_CUDA(cudaStreamSynchronize(ctx->stream));
   return B2_OK;
 }
+int b2_copy_d2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (int r = use_device(ctx)) return r;
+  B2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));   // asynchronous: ordered on the stream
+  return B2_OK;
+}
 int b2_dev_memset(b2_ctx* ctx, void* dst, int value, size_t bytes) {
   if (int r = use_device(ctx)) return r;
   B2_CUDA(cudaMemsetAsync(dst, value, bytes, ctx->stream));

@@ -94,6 +94,8 @@ int b2_host_alloc(b2_ctx* ctx, size_t bytes, void** out); /* pinned */
 int b2_host_free(b2_ctx* ctx, void* p);
 int b2_copy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
 int b2_copy_d2h(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* sync on return */
+int b2_copy_d2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes); /* on the context's stream, asynchronous: bench.py
+                                                                         times it as this box's own copy bandwidth */
 int b2_dev_memset(b2_ctx* ctx, void* dst, int value, size_t bytes);
 /* DataFrame columns -> row-major float32 rows in HBM.  reference: stage_1_train_model.py:95-96
  * (`X = data['X'].values.reshape(-1, 1)`): pandas hands every column over as its own strided array.  cols[j] = address of
