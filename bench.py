@@ -346,7 +346,12 @@ def main() -> None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-        if os.environ.get("B2_NO_P2P") != "1" and world <= 8:
+        # which exchange: measured on 8 GPUs, alternating runs on one box (profiles/r02_exchange_n8_diag.txt): NCCL 1.18-1.20 ms
+        # per fit, the peer-memory exchange 1.39-1.51 ms (its system-scope fences do not scale with the number of peers);
+        # at 2 and 4 GPUs the two are within 1-2 %.  So: peer-memory exchange up to 4 ranks, NCCL beyond;
+        # B2_FORCE_P2P=1 / B2_NO_P2P=1 override.
+        want_p2p = os.environ.get("B2_NO_P2P") != "1" and world <= 8 and (world <= 4 or os.environ.get("B2_FORCE_P2P") == "1")
+        if want_p2p:
             # one-shot peer-memory exchange of S (NVLink stores + flags) fused into the Gram / solve kernels
             try:
                 mine = ctx.comm_p2p_export()
@@ -368,7 +373,9 @@ def main() -> None:
                 ctx.comm_p2p_detach()
                 exchange_note = (exchange_note or "a peer could not attach") + "; NCCL all-reduce used"
         else:
-            exchange_note = "B2_NO_P2P=1: NCCL all-reduce"
+            exchange_note = ("B2_NO_P2P=1: NCCL all-reduce" if os.environ.get("B2_NO_P2P") == "1" else
+                             f"{world} ranks: NCCL all-reduce (measured faster than the peer-memory exchange beyond 4 ranks; "
+                             f"B2_FORCE_P2P=1 selects the latter)")
         if exchange_note:
             print(f"[bench] {exchange_note}", file=sys.stderr)
 

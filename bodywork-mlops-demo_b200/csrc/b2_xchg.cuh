@@ -6,8 +6,8 @@
 //     u32    flag[kMaxRanks]                                 flag[r] = last exchange whose slot r is complete here
 //     u32    ticket (word 32), status (word 48)
 // A producer stores its partial into slot[e & 1][rank] of EVERY buffer (st.global on peer pointers: NVLink 5 /
-// NVSwitch), fences at system scope and then writes e into flag[rank] of every buffer (st.release.sys); a consumer waits
-// (ld.acquire.sys) until all flags of its OWN buffer carry e and sums the slots in rank order (bit-identical on every rank).  Slots are double
+// NVSwitch), fences at system scope and then writes e into flag[rank] of every buffer; a consumer waits until all
+// flags of its OWN buffer carry e and sums the slots in rank order (bit-identical on every rank).  Slots are double
 // buffered by parity: a rank can be at most one exchange ahead of a peer (its next wait needs that peer's next flag).
 #pragma once
 #include "b2_internal.cuh"
@@ -37,26 +37,28 @@ __device__ __forceinline__ void xchg_store_all(const PeerPtrs& peers, int n_rank
 // (__threadfence_system by the storing threads, then a block/grid level "all done" such as a ticket).
 __device__ __forceinline__ void xchg_publish(const PeerPtrs& peers, int n_ranks, int rank, unsigned int epoch) {
   if ((int)threadIdx.x < n_ranks) {
-    unsigned int* f = xchg_flags(peers.p[threadIdx.x]) + rank;            // "rank has delivered exchange `epoch`"
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    volatile unsigned int* f = xchg_flags(peers.p[threadIdx.x]) + rank;   // "rank has delivered exchange `epoch`"
+    *f = epoch;
+    __threadfence_system();
   }
 }
 
 // One thread: wait until every rank's slot of exchange `epoch` is complete in the own buffer.  Bounded by
 // %globaltimer: a dead or very late peer yields `false` (and a status word the host reads), never a hung GPU.
 __device__ __forceinline__ bool xchg_wait(double* own, int n_ranks, unsigned int epoch, unsigned long long timeout_ns) {
-  const unsigned int* f = xchg_flags(own);
+  volatile unsigned int* f = xchg_flags(own);
   const unsigned long long t0 = globaltimer_ns();
   for (int r = 0; r < n_ranks; ++r) {
     unsigned int spins = 0;
-    while (true) {
-      unsigned int v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + r) : "memory");
-      if ((int)(v - epoch) >= 0) break;                                 // exchange numbers are monotonic
-      if ((++spins & 1023u) == 0u && globaltimer_ns() - t0 > timeout_ns) return false;
+    while ((int)(f[r] - epoch) < 0) {                                   // exchange numbers are monotonic
+      if ((++spins & 63u) == 0u) {
+        if (globaltimer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(200);
+      }
     }
   }
+  __threadfence_system();
   return true;
 }
 
