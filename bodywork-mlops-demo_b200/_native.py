@@ -54,6 +54,7 @@ _SIGNATURES = {
     "b2_gram_import": (C.c_int, [_vp, _vp, C.c_int]),
     "b2_split_mask": (C.c_int, [_c_i64, _c_i64, C.c_uint32, _vp]),
     "b2_copy_d2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "b2_pack_columns": (C.c_int, [_vp, _vp, C.c_int, _c_i64, C.c_int, _vp]),
     "b2_upload_columns": (C.c_int, [_vp, _vp, _vp, C.c_int, _c_i64, C.c_int, _vp]),
     "b2_fit": (C.c_int, [_vp, _vp, C.c_int, _vp, _c_i64, C.c_int, _c_i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp,
                          C.POINTER(C.c_double)]),
@@ -131,6 +132,22 @@ def device_count() -> int:
     n = C.c_int(0)
     rc = load().b2_device_count(C.byref(n))
     return int(n.value) if rc == 0 else 0
+
+
+def pack_columns(columns) -> np.ndarray:
+    """1-D host columns (all float64 or all float32, any stride) -> row-major float32 (n, d): ``b2_pack_columns``, the
+    multi-threaded gather + conversion ``Context.upload_columns`` runs on the way to the device (host only, no GPU)."""
+    cols = [np.asarray(c) for c in columns]
+    if not cols or any(c.ndim != 1 or c.shape != cols[0].shape or c.dtype != cols[0].dtype for c in cols) \
+            or cols[0].dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise RuntimeError("pack_columns: 1-D columns of one length and one dtype (float64 or float32) expected")
+    n, d = int(cols[0].shape[0]), len(cols)
+    out = np.empty((n, d), dtype=np.float32)
+    ptrs = (C.c_void_p * d)(*[c.ctypes.data for c in cols])
+    strides = (C.c_int64 * d)(*[c.strides[0] if n > 1 else c.itemsize for c in cols])
+    _check(load().b2_pack_columns(C.cast(ptrs, C.c_void_p), C.cast(strides, C.c_void_p),
+                                  F64 if cols[0].dtype == np.float64 else F32, n, d, out.ctypes.data), "b2_pack_columns")
+    return out
 
 
 def to_bf16_bits(a: np.ndarray) -> np.ndarray:

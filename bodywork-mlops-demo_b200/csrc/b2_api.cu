@@ -447,6 +447,39 @@ int b2_copy_h2d(b2_ctx* ctx, void* dst, const void* src, size_t bytes) {
 // time once the fit takes a millisecond.  Here the host threads of the bounce ring gather 16 columns at a time into the
 // pinned bounce block (full 64-byte lines written, every column read as its own sequential stream), converting on the fly,
 // while the previous block is on the wire.
+// the gather + conversion alone, host to host (no device needed): rows [0, n_rows) of d strided columns -> out[n_rows][d]
+static int pack_columns_threads(float* dst, const void* const* cols, const int64_t* strides, int dtype, int64_t r0, int64_t rows,
+                                int d) {
+  const int nt = copy_threads();
+  auto work = [=](int t) {
+    const int64_t lo = rows * t / nt / 64 * 64, hi = (t == nt - 1) ? rows : rows * (t + 1) / nt / 64 * 64;
+    if (hi <= lo) return;
+    if (dtype == B2_F64) pack_rows<double>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
+    else pack_rows<float>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
+  };
+  if (rows < 4096 || nt == 1) {
+    if (dtype == B2_F64) pack_rows<double>(dst, cols, strides, r0, rows, d); else pack_rows<float>(dst, cols, strides, r0, rows, d);
+    return B2_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  return B2_OK;
+}
+
+int b2_pack_columns(const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d, float* out) {
+  if (cols == nullptr || strides == nullptr || out == nullptr || n_rows < 0 || d < 1 || d > kMaxD ||
+      (dtype != B2_F32 && dtype != B2_F64)) {
+    set_error("b2_pack_columns: bad arguments (1 <= d <= %d, dtype B2_F32 or B2_F64)", kMaxD);
+    return B2_E_ARG;
+  }
+  for (int j = 0; j < d; ++j)
+    if (cols[j] == nullptr) { set_error("b2_pack_columns: column %d is null", j); return B2_E_ARG; }
+  return pack_columns_threads(out, cols, strides, dtype, 0, n_rows, d);
+}
+
 int b2_upload_columns(b2_ctx* ctx, const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d,
                       float* X_dev) {
   if (int r = use_device(ctx)) return r;
@@ -459,27 +492,12 @@ int b2_upload_columns(b2_ctx* ctx, const void* const* cols, const int64_t* strid
     if (cols[j] == nullptr) { set_error("b2_upload_columns: column %d is null", j); return B2_E_ARG; }
   if (int r = ensure_staging(ctx)) return r;
   if (int r = ensure_bounce(ctx)) return r;
-  const int nt = copy_threads();
   int buf = 0;
   for (int64_t r0 = 0; r0 < n_rows; r0 += ctx->stage_rows, buf ^= 1) {
     const int64_t rows = n_rows - r0 < ctx->stage_rows ? n_rows - r0 : ctx->stage_rows;
     B2_CUDA(cudaEventSynchronize(ctx->ev_bounce[buf]));               // the H2D that last read this bounce block is done
     float* dst = static_cast<float*>(ctx->bounce[buf]);
-    auto work = [=](int t) {
-      const int64_t lo = rows * t / nt / 64 * 64, hi = (t == nt - 1) ? rows : rows * (t + 1) / nt / 64 * 64;
-      if (hi <= lo) return;
-      if (dtype == B2_F64) pack_rows<double>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
-      else pack_rows<float>(dst + (size_t)lo * d, cols, strides, r0 + lo, hi - lo, d);
-    };
-    if (rows < 4096 || nt == 1) {
-      if (dtype == B2_F64) pack_rows<double>(dst, cols, strides, r0, rows, d); else pack_rows<float>(dst, cols, strides, r0, rows, d);
-    } else {
-      std::vector<std::thread> pool;
-      pool.reserve(nt - 1);
-      for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
-      work(0);
-      for (auto& th : pool) th.join();
-    }
+    pack_columns_threads(dst, cols, strides, dtype, r0, rows, d);
     B2_CUDA(cudaMemcpyAsync(X_dev + (size_t)r0 * d, dst, (size_t)rows * d * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
     B2_CUDA(cudaEventRecord(ctx->ev_bounce[buf], ctx->copy_stream));
   }

@@ -104,6 +104,9 @@ int b2_dev_memset(b2_ctx* ctx, void* dst, int value, size_t bytes);
  * while the previous block is on the wire; sync on return. */
 int b2_upload_columns(b2_ctx* ctx, const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d,
                       float* X_dev);
+/* The gather + conversion of b2_upload_columns alone, host to host (no device, no context): out[n_rows][d] float32, e.g. a
+ * caller's own pinned block.  Multi-threaded like the upload. */
+int b2_pack_columns(const void* const* cols, const int64_t* strides, int dtype, int64_t n_rows, int d, float* out);
 
 /* ---- Gram accumulation: replaces LinearRegression.fit's pass over the rows -----------------
  * reference: stage_1_train_model.py:105-106 -> sklearn/linear_model/_base.py (centre + gelsd). */

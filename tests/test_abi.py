@@ -232,3 +232,24 @@ def test_service_test_metrics_algebra_matches_stage_4_definitions():
     import pandas as pd
     df = pd.DataFrame({"score": score, "label": label})          # the reference's own pandas expressions
     assert rec["r_squared"].iloc[0] == pytest.approx(df.score.corr(df.label), rel=1e-10)
+
+
+def test_pack_columns_gathers_and_converts_like_numpy():
+    """b2_pack_columns (host only): strided float64 / float32 columns -> np.stack(columns, 1).astype(float32), bit for bit,
+    across the thread split (n above and below the 4 096-row single-thread cut, not a multiple of 64) -- the gather
+    b2_upload_columns runs on the way to the device."""
+    rng = np.random.RandomState(0)
+    for n, d, dtype in ((1, 1, np.float64), (100, 3, np.float64), (5000, 7, np.float32), (70_001, 128, np.float64),
+                        (33_333, 17, np.float64)):
+        block = (rng.rand(d, n) * 100 - 50).astype(dtype)              # pandas: one (d, n) block, contiguous columns
+        cols = [block[j] for j in range(d)]
+        if d >= 3:
+            cols[1] = (rng.rand(2 * n) * 100).astype(dtype)[::2]           # a strided column
+            cols[2] = np.asfortranarray(rng.rand(n, 2).astype(dtype))[:, 1]
+        got = b2.native.pack_columns(cols)
+        assert got.dtype == np.float32 and got.shape == (n, d)
+        assert np.array_equal(got, np.stack(cols, axis=1).astype(np.float32)), (n, d)
+    with pytest.raises(RuntimeError):
+        b2.native.pack_columns([np.zeros(4), np.zeros(5)])
+    with pytest.raises(RuntimeError):
+        b2.native.pack_columns([np.zeros(4, np.int32)])
