@@ -4,8 +4,10 @@
 One "step" = one complete fit of the resident rows through the C-ABI (b2_fit): four kernel launches --
     tc_shift_kernel     per-column shift from a 2048-row sample
     gram_tc_kernel      tcgen05 Gram over every row of this rank's shard (the roofline kernel)
-    tc_finalize_kernel  reduce the per-CTA partials, fold into S, store S into every peer's exchange slot over NVLink (N > 1)
-    solve kernel        waits for the peers' slots and sums them (N > 1), LDL^T, coefficients written to pinned host memory
+    tc_finalize_kernel  reduce the per-CTA partials, fold into S, store S into every peer's exchange slot over NVLink (2-4 GPUs)
+    solve kernel        waits for the peers' slots and sums them (2-4 GPUs), LDL^T, coefficients written to pinned host memory
+At more than 4 GPUs the exchange is one ncclAllReduce of S between the finalize and the solve kernel instead: measured faster
+there (profiles/r02_exchange_n8_diag.txt); `exchange.exchange_used` says which ran, B2_FORCE_P2P=1 / B2_NO_P2P=1 override.
 
 Arms
     python bench.py [--gpus N --steps K --warmup W]          this repo (one process per GPU under torchrun)
