@@ -249,6 +249,16 @@ def test_pack_columns_gathers_and_converts_like_numpy():
         got = b2.native.pack_columns(cols)
         assert got.dtype == np.float32 and got.shape == (n, d)
         assert np.array_equal(got, np.stack(cols, axis=1).astype(np.float32)), (n, d)
+    # row-major float64 matrix (the estimator's view list), reversed rows (negative stride), a broadcast column (stride 0),
+    # non-finite and out-of-float32-range values: the conversion is numpy's, element by element
+    X = rng.rand(9001, 20) * 1e3
+    X[5, 3], X[6, 3], X[7, 3], X[8, 3], X[9, 3] = np.nan, np.inf, -np.inf, 1e300, -1e-300
+    cols = [X[:, j] for j in range(20)]
+    cols[4] = X[::-1, 4]
+    cols[5] = np.broadcast_to(np.float64(2.5), (9001,))
+    with np.errstate(over="ignore"):
+        want = np.stack(cols, axis=1).astype(np.float32)
+    assert np.array_equal(b2.native.pack_columns(cols), want, equal_nan=True)
     with pytest.raises(RuntimeError):
         b2.native.pack_columns([np.zeros(4), np.zeros(5)])
     with pytest.raises(RuntimeError):
